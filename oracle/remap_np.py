@@ -134,8 +134,11 @@ def weight_table(interpolation: int) -> np.ndarray:
             v = (one[ay][:, None] * one[ax][None, :]).astype(np.float32)
             it = np.clip(np.rint((v * np.float32(COEF_SCALE)).astype(np.float32)), -32768, 32767).astype(np.int64)
             diff = int(it.sum()) - COEF_SCALE
-            assert diff == 0 or k > 2
-            if diff != 0:  # never taken for LINEAR: every product of n/32 fractions is exact
+            if diff != 0 and k == 2:
+                # LINEAR: only (ax,ay)=(0,0) saturates (32768 -> 32767); OpenCV ends with {32767,0,0,1}, which
+                # cannot change a uint8 result (remap() uses the closed 10-bit form for LINEAR anyway)
+                it[1, 1] -= diff
+            elif diff != 0:
                 mk1 = mk2 = Mk1 = Mk2 = k2
                 for k1 in range(k2, k2 + 2):
                     for kk in range(k2, k2 + 2):
