@@ -1,0 +1,325 @@
+"""GPU parity tests (-m gpu, run on the B200 box): the CUDA path through the C ABI against the golden vectors of
+the unmodified reference, against the oracle on seeded inputs, and through size-independent properties at the
+full BASELINE.json sizes.  Nothing here reads /root/reference.
+
+Tolerances (BASELINE.json north_star): maps within 1e-4 px of the reference chain (asserted as: bit-identical
+float32 except for at most a vanishing number of 1-ulp round-to-nearest flips); sampled uint8 pixels BIT-EXACT
+for every interpolation whenever the maps are identical.
+"""
+from __future__ import annotations
+
+import cv2
+import numpy as np
+import pytest
+
+import vr180_convert_b200 as V
+from oracle import chain_np, remap_np
+from tests.conftest import disc_frame
+
+pytestmark = pytest.mark.gpu
+
+NS = {k: getattr(V, k) for k in V.__all__}
+NS["np"] = np
+
+
+def _ulp_diff(a, b):
+    ai = a.view(np.int32).astype(np.int64)
+    bi = b.view(np.int32).astype(np.int64)
+    ai = np.where(ai < 0, -(2**31) - ai, ai)
+    bi = np.where(bi < 0, -(2**31) - bi, bi)
+    return np.abs(ai - bi)
+
+
+def _assert_maps_close(got, want, what, max_flip_frac=1e-5):
+    assert got.shape == want.shape and got.dtype == np.float32, what
+    nan_g, nan_w = np.isnan(got), np.isnan(want)
+    # a NaN appears where float64 rounding pushed |v_z| just above 1; allow the GPU's
+    # libm to disagree on a vanishing number of such singular pixels
+    assert (nan_g != nan_w).sum() <= max(1, int(want.size * 1e-6)), what
+    ok = ~(nan_g | nan_w)
+    d = np.abs(got[ok].astype(np.float64) - want[ok].astype(np.float64))
+    ulps = _ulp_diff(got[ok], want[ok])
+    tol = 1e-4 + np.spacing(np.abs(want[ok]).astype(np.float32)).astype(np.float64)
+    assert (d <= tol).all(), (what, float(d.max()))
+    assert ulps.max(initial=0) <= 1, (what, int(ulps.max()))
+    assert (ulps > 0).mean() <= max_flip_frac + 1.0 / max(ulps.size, 1), (what, float((ulps > 0).mean()))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# (1) analytic maps  vs  reference get_map
+# ---------------------------------------------------------------------------------------------------------
+def test_get_map_matches_reference_golden(golden_maps):
+    z, meta = golden_maps
+    for name, case in meta["cases"].items():
+        t = eval(case["expr"], NS)  # noqa: S307
+        for si, (size_out, size_in, radius) in enumerate(meta["shapes"]):
+            xm, ym = V.get_map(t, radius=radius, size_input=tuple(size_in), size_output=tuple(size_out))
+            # small maps: tolerate one flipped element per map
+            _assert_maps_close(xm, z[f"{name}/{si}/x"], (name, si, "x"), max_flip_frac=2e-3)
+            _assert_maps_close(ym, z[f"{name}/{si}/y"], (name, si, "y"), max_flip_frac=2e-3)
+
+
+def test_get_map_survey_known_answers():
+    xm, ym = V.get_map(V.EquirectangularEncoder() * V.FisheyeDecoder("equidistant"), radius=128.0,
+                       size_input=(256, 256), size_output=(256, 256))
+    assert (xm[0, 0], ym[0, 0]) == (128.0, 0.0) and (xm[128, 128], ym[128, 128]) == (128.0, 128.0)
+    assert xm[37, 201].view(np.uint32) == 0x432585C3 and ym[37, 201].view(np.uint32) == 0x41EC3D23
+    assert xm[255, 255].view(np.uint32) == 0x4301920C and ym[255, 255].view(np.uint32) == 0x437FFA64
+
+
+@pytest.mark.parametrize("name,n", [("base", 2048), ("rot_poly", 4096)])
+def test_get_map_fullsize_samples(golden_fullsize, golden_maps, name, n):
+    """cfg2 / cfg3 sizes: sparse samples + one full row/column of the reference's maps."""
+    _, meta = golden_maps
+    t = eval(meta["cases"][name]["expr"], NS)  # noqa: S307
+    xm, ym = V.get_map(t, radius=n / 2, size_input=(n, n), size_output=(n, n))
+    z = golden_fullsize
+    idx = z[f"{name}/{n}/idx"]
+    _assert_maps_close(xm[idx[:, 0], idx[:, 1]], z[f"{name}/{n}/x"], (name, "x samples"), 1e-3)
+    _assert_maps_close(ym[idx[:, 0], idx[:, 1]], z[f"{name}/{n}/y"], (name, "y samples"), 1e-3)
+    _assert_maps_close(np.stack([xm[n // 3], ym[n // 3]]), z[f"{name}/{n}/row"], (name, "row"), 1e-3)
+    _assert_maps_close(np.stack([xm[:, n // 5], ym[:, n // 5]]), z[f"{name}/{n}/col"], (name, "col"), 1e-3)
+
+
+def test_get_map_vs_oracle_whole_map():
+    """Whole 1024^2 map against the oracle chain on this host (rotated + polynomial chain)."""
+    q = (0.9999093510664558, 0.00500054686470522, 0.01000109372941044, -0.00750082029705783)
+    t = (V.EquirectangularEncoder() * V.Euclidean3DRotator(V.quaternion(*q)) * V.PolynomialScaler([0, 1, -0.02, 0.003])
+         * V.FisheyeDecoder("equidistant"))
+    ops = [("equirect_enc", True), ("rot3", chain_np.quat_to_matrix(*q).ravel().tolist()),
+           ("poly", [0, 1, -0.02, 0.003]), ("fisheye_dec", "equidistant")]
+    n = 1024
+    xm, ym = V.get_map(t, radius=n / 2, size_input=(n, n), size_output=(n, n))
+    wx, wy = chain_np.get_map(ops, radius=n / 2, size_input=(n, n), size_output=(n, n))
+    _assert_maps_close(xm, wx, "x")
+    _assert_maps_close(ym, wy, "y")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# (2) sampling  vs  cv2.remap
+# ---------------------------------------------------------------------------------------------------------
+def test_remap_matches_cv2_golden(golden_remap):
+    g = golden_remap
+    src, xm, ym = g["src"], g["xmap"], g["ymap"]
+    for interp in (0, 1, 2, 4):
+        for bm in (0, 1, 2, 3, 4):
+            for bi, bv in enumerate((0, 7, (3, 200, 90))):
+                got = V.remap_maps(src, xm, ym, interpolation=interp, border_mode=bm, border_value=bv)
+                assert np.array_equal(got, g[f"out/{interp}/{bm}/{bi}"]), (interp, bm, bi)
+
+
+@pytest.mark.parametrize("channels", [1, 3, 4])
+@pytest.mark.parametrize("interp", [0, 1, 2, 4])
+def test_remap_random_maps_vs_oracle(channels, interp):
+    rng = np.random.default_rng(100 * channels + interp)
+    src = rng.integers(0, 256, (61, 83, channels), dtype=np.uint8)
+    if channels == 1:
+        src = src[:, :, 0]
+    h, w = 77, 130
+    xm = (rng.random((h, w)) * 100 - 9).astype(np.float32)
+    ym = (rng.random((h, w)) * 80 - 9).astype(np.float32)
+    xm[0, :6] = [np.nan, np.inf, -np.inf, 1e9, -7e7, 6e7]
+    ym[1, :6] = [np.nan, np.inf, -np.inf, 1e9, -7e7, 6e7]
+    xm[2] = np.floor(xm[2]) + 1 / 64  # exact .5 ties of x*32
+    for bm in (0, 1, 2, 3, 4):
+        bv = (5, 60, 200, 9)[:channels] if channels > 1 else 5
+        want = remap_np.remap(src, xm, ym, interp, bm, bv)
+        got = V.remap_maps(src, xm, ym, interpolation=interp, border_mode=bm, border_value=bv)
+        assert np.array_equal(got, want), (channels, interp, bm)
+        assert np.array_equal(want, cv2.remap(src, xm, ym, interpolation=interp, borderMode=bm, borderValue=bv))
+
+
+def test_remap_strided_view_and_empty_edges():
+    rng = np.random.default_rng(5)
+    big = rng.integers(0, 256, (50, 120, 3), dtype=np.uint8)
+    view = big[:, 60:]  # row-strided half, as remapper.py:455-456 produces
+    xm = (rng.random((40, 33)) * 70 - 5).astype(np.float32)
+    ym = (rng.random((40, 33)) * 60 - 5).astype(np.float32)
+    assert np.array_equal(V.remap_maps(view, xm, ym, interpolation=1), cv2.remap(view, xm, ym, interpolation=1))
+    # 1-pixel source and 1x1 destination
+    one = np.full((1, 1, 3), 77, np.uint8)
+    m0 = np.zeros((1, 1), np.float32)
+    for interp in (0, 1, 2, 4):
+        assert np.array_equal(V.remap_maps(one, m0, m0, interpolation=interp, border_mode=1),
+                              cv2.remap(one, m0, m0, interpolation=interp, borderMode=1))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# (3) get_radius
+# ---------------------------------------------------------------------------------------------------------
+def test_get_radius_golden(golden_radius):
+    for key, want in golden_radius.items():
+        if key[0].isdigit():
+            h, w, r = map(int, key.split("x"))
+            yy, xx = np.mgrid[:h, :w]
+            img = np.where(((xx - w // 2) ** 2 + (yy - h // 2) ** 2 <= r * r)[..., None], 200, 0).astype(np.uint8)
+            img = np.repeat(img, 3, axis=2)
+            assert V.get_radius(img) == want, key
+    for img in (np.zeros((64, 64, 3), np.uint8), np.full((64, 64, 3), 255, np.uint8)):
+        with pytest.raises(IndexError):
+            V.get_radius(img)
+
+
+def test_get_radius_random_lines_vs_oracle():
+    rng = np.random.default_rng(11)
+    for trial in range(20):
+        h, w = int(rng.integers(20, 300)), int(rng.integers(20, 300))
+        img = rng.integers(0, 40, (h, w, 3), dtype=np.uint8)  # values straddle the threshold sum of 30
+        thr = int(rng.integers(5, 15))
+        try:
+            want = chain_np.get_radius(img, threshold=thr)
+        except IndexError:
+            with pytest.raises(IndexError):
+                V.get_radius(img, threshold=thr)
+            continue
+        assert V.get_radius(img, threshold=thr) == want, (trial, h, w)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# (4) apply / apply_lr end to end  vs  the reference's outputs
+# ---------------------------------------------------------------------------------------------------------
+def test_apply_lr_matches_reference_golden(golden_apply, golden_maps, tmp_path):
+    g = golden_apply
+    _, meta = golden_maps
+    card = g["card"]
+    left, right = card[:, :128], card[:, 128:]
+    for key in g.files:
+        if not key.startswith("lr/"):
+            continue
+        _, name, interp, radius = key.split("/")
+        radius = radius if radius in ("max", "auto") else float(radius)
+        t = eval(meta["cases"][name]["expr"], NS)  # noqa: S307
+        out = tmp_path / "o.png"
+        V.apply_lr(t, left_path=left, right_path=right, out_path=out, size_output=(96, 80),
+                   interpolation=int(interp), radius=radius)
+        got = cv2.imread(str(out))
+        assert got.shape == g[key].shape == (80, 192, 3)
+        assert np.array_equal(got, g[key]), key
+    tl = eval(meta["cases"]["rot_poly"]["expr"], NS)  # noqa: S307
+    tr = eval(meta["cases"]["rot_nonunit"]["expr"], NS)  # noqa: S307
+    got = V.lr_frame((tl, tr), left, right, size_output=(96, 80), interpolation=1, radius="auto")
+    assert np.array_equal(got, g["lr_tuple/rot_poly+rot_nonunit/1/auto"])
+    imgs = V.apply(eval(meta["cases"]["fe_poly"]["expr"], NS), in_paths=[card, card[::-1].copy()],  # noqa: S307
+                   size_output=(72, 72), interpolation=1, radius="max", boarder_value=9)
+    assert np.array_equal(imgs[0], g["apply/fe_poly/0"]) and np.array_equal(imgs[1], g["apply/fe_poly/1"])
+
+
+def test_apply_lr_same_path_splits_halves(tmp_path, golden_apply):
+    """remapper.py:448-456: identical paths -> one file split into halves."""
+    card = golden_apply["card"]
+    src = tmp_path / "sbs.png"
+    cv2.imwrite(str(src), card)
+    out = tmp_path / "out.png"
+    t = V.EquirectangularEncoder() * V.FisheyeDecoder("equidistant")
+    V.apply_lr(t, left_path=src, right_path=src, out_path=out, size_output=(64, 64), interpolation=1, radius="max")
+    want = V.lr_frame(t, card[:, :128], card[:, 128:], size_output=(64, 64), interpolation=1, radius="max")
+    assert np.array_equal(cv2.imread(str(out)), want)
+
+
+def test_user_defined_transformer_goes_through_lut_path():
+    class Mine(V.PolarRollTransformer):  # README.md:204-219
+        def transform_polar(self, theta, roll, **kwargs):
+            return theta**0.98 + theta**1.01, roll
+
+    t = V.EquirectangularEncoder() * Mine() * V.FisheyeDecoder("equidistant")
+    img = disc_frame(96, 96, seed=4)
+    got = V.apply(t, in_paths=img, size_output=(64, 64), interpolation=1, radius=40.0)[0]
+    xm, ym = np.meshgrid(np.arange(64), np.arange(64))
+    fx, fy = (V.NormalizeTransformer() * t * V.DenormalizeTransformer(scale=(40.0, 40.0), center=(48, 48))).transform(xm, ym)
+    want = cv2.remap(img, fx.astype(np.float32), fy.astype(np.float32), interpolation=1)
+    assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# (5) batched device-resident path (SbsWarper): analytic == LUT == fixed LUT == oracle
+# ---------------------------------------------------------------------------------------------------------
+def _frames(n, h, w, seed0=0):
+    return np.stack([disc_frame(h, w, seed=seed0 + i) for i in range(n)])
+
+
+@pytest.mark.parametrize("interp", [0, 1, 2, 4])
+def test_sbs_warper_sources_agree_and_match_oracle(interp):
+    import torch
+
+    n, hin, win, wout, hout = 5, 160, 160, 128, 96
+    q = (0.9999093510664558, 0.00500054686470522, 0.01000109372941044, -0.00750082029705783)
+    t = (V.EquirectangularEncoder() * V.Euclidean3DRotator(V.quaternion(*q)) * V.PolynomialScaler([0, 1, -0.02, 0.003])
+         * V.FisheyeDecoder("equidistant"))
+    left = torch.from_numpy(_frames(n, hin, win, 0)).cuda()
+    right = torch.from_numpy(_frames(n, hin, win, 100)).cuda()
+    outs = {}
+    for src in ("analytic", "lut", "lut_fixed"):
+        if src == "lut_fixed" and interp == 0:
+            continue
+        wp = V.SbsWarper(t, size_input=(hin, win), size_output=(wout, hout), interpolation=interp, radius=80.0,
+                         map_source=src)
+        outs[src] = wp(left, right).cpu().numpy()
+    for src in outs:
+        assert np.array_equal(outs[src], outs["analytic"]), src
+    # oracle: reference chain restatement + cv2.remap per eye + concatenate
+    ops = [("equirect_enc", True), ("rot3", chain_np.quat_to_matrix(*q).ravel().tolist()),
+           ("poly", [0, 1, -0.02, 0.003]), ("fisheye_dec", "equidistant")]
+    xm, ym = chain_np.get_map(ops, radius=80.0, size_input=(hin, win), size_output=(wout, hout))
+    ln, rn = left.cpu().numpy(), right.cpu().numpy()
+    for f in range(n):
+        want = np.concatenate([cv2.remap(ln[f], xm, ym, interpolation=interp),
+                               cv2.remap(rn[f], xm, ym, interpolation=interp)], axis=1)
+        assert np.array_equal(outs["analytic"][f], want), (interp, f)
+
+
+def test_sbs_warper_per_eye_tuple_and_auto_radius():
+    import torch
+
+    n, hin, win, wout, hout = 3, 200, 200, 96, 96
+    tl = V.EquirectangularEncoder() * V.Euclidean3DRotator(V.from_rotation_vector([0.01, 0.02, -0.015])) * V.FisheyeDecoder("equidistant")
+    tr = V.EquirectangularEncoder() * V.Euclidean3DRotator(V.from_rotation_vector([-0.01, -0.02, 0.015])) * V.FisheyeDecoder("equidistant")
+    frames_l, frames_r = _frames(n, hin, win, 0), _frames(n, hin, win, 50)
+    frames_r[1, :, :, :] = 0
+    yy, xx = np.ogrid[:hin, :win]
+    frames_r[1][(xx - 100) ** 2 + (yy - 100) ** 2 <= 70 * 70] = 123  # a smaller disc in one right frame
+    left, right = torch.from_numpy(frames_l).cuda(), torch.from_numpy(frames_r).cuda()
+    # per-eye tuple, fixed radius
+    wp = V.SbsWarper((tl, tr), size_input=(hin, win), size_output=(wout, hout), interpolation=1, radius=95.0)
+    got = wp(left, right).cpu().numpy()
+    for f in range(n):
+        want = V.lr_frame((tl, tr), frames_l[f], frames_r[f], size_output=(wout, hout), interpolation=1, radius=95.0)
+        assert np.array_equal(got[f], want)
+    # auto radius per frame, consumed on the device
+    wp = V.SbsWarper(tl, size_input=(hin, win), size_output=(wout, hout), interpolation=2, radius="auto")
+    got = wp(left, right).cpu().numpy()
+    rad, trans = wp.radius_per_frame(left, right)
+    rad = rad.cpu().numpy()
+    for f in range(n):
+        want_r = max(chain_np.get_radius(frames_l[f]), chain_np.get_radius(frames_r[f]))
+        assert rad[f] == want_r
+        want = V.lr_frame(tl, frames_l[f], frames_r[f], size_output=(wout, hout), interpolation=2, radius="auto")
+        assert np.array_equal(got[f], want), f
+
+
+# ---------------------------------------------------------------------------------------------------------
+# (6) full BASELINE sizes through size-independent properties
+# ---------------------------------------------------------------------------------------------------------
+def test_fullsize_8k_pair_properties():
+    """cfg3-sized pair (2 x 4096^2 -> 8192 x 4096): (a) identity-like check against cv2 on the GPU-built maps,
+    (b) both eyes land in their halves, (c) batch invariance (frame f of a batch == the same frame alone)."""
+    import torch
+
+    n = 4096
+    q = V.from_rotation_vector([0.01, 0.02, -0.015])
+    t = V.EquirectangularEncoder() * V.Euclidean3DRotator(q) * V.PolynomialScaler([0, 1, -0.02, 0.003]) * V.FisheyeDecoder("equidistant")
+    fl, fr = disc_frame(n, n, 0), disc_frame(n, n, 1)
+    left = torch.from_numpy(np.stack([fl, fr])).cuda()
+    right = torch.from_numpy(np.stack([fr, fl])).cuda()
+    wp = V.SbsWarper(t, size_input=(n, n), size_output=(n, n), interpolation=1, radius=n / 2)
+    out = wp(left, right)
+    assert out.shape == (2, n, 2 * n, 3)
+    # (c) swapping the eyes swaps the halves, bit for bit
+    assert torch.equal(out[0, :, :n], out[1, :, n:]) and torch.equal(out[0, :, n:], out[1, :, :n])
+    # (a) fused analytic output == cv2.remap driven by the GPU-built float32 maps (pixel exactness given the maps)
+    maps = wp.maps()[0].cpu().numpy()
+    want = cv2.remap(fl, maps[0], maps[1], interpolation=1)
+    assert np.array_equal(out[0, :, :n].cpu().numpy(), want)
+    # checksum of checksums: LUT and fixed-LUT sources give the same frame
+    for src in ("lut", "lut_fixed"):
+        other = V.SbsWarper(t, size_input=(n, n), size_output=(n, n), interpolation=1, radius=n / 2, map_source=src)
+        assert torch.equal(other(left[:1], right[:1])[0], out[0])

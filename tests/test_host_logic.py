@@ -1,0 +1,167 @@
+"""CPU tests (-m "not gpu") of the host side: transformer algebra, lowering to the chain descriptor, the C-ABI
+library (loads, exports every declared symbol, host-only entry points), frame sharding."""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import vr180_convert_b200 as V
+from oracle import chain_np, remap_np
+from vr180_convert_b200 import _native as N
+from vr180_convert_b200.remapper import lower_full
+
+ROOT = Path(__file__).resolve().parent.parent
+NS = {k: getattr(V, k) for k in V.__all__}
+NS["np"] = np
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "vr180_b200.h").read_text()
+    declared = set(re.findall(r"^\s*(?:int|uint64_t|const char\*)\s+(vr180_\w+)\s*\(", header, flags=re.M))
+    assert declared, "no declarations parsed"
+    handle = N.lib()
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in include/vr180_b200.h but not exported"
+        assert name in N.SYMBOLS, f"{name} has no ctypes prototype"
+    assert handle.vr180_abi_version() == 1
+    assert handle.vr180_status_string(-5) == b"malformed chain descriptor"
+    assert isinstance(handle.vr180_launch_count(), int)
+
+
+def test_struct_sizes_match_header_layout():
+    # natural-alignment layouts of include/vr180_b200.h
+    assert C.sizeof(N.Op) == 8 + 8 * 12
+    assert C.sizeof(N.Chain) == 8 + 12 * C.sizeof(N.Op)
+    assert C.sizeof(N.Image) == 40
+    assert C.sizeof(N.MapSrc) == 56
+    assert C.sizeof(N.View) == 40 + 56 + 8
+    assert C.sizeof(N.RemapParams) == 8 + 2 * 104 + 24 + 24
+
+
+def test_weight_tables_match_oracle():
+    """The host-built cubic / lanczos4 tables the kernels use == the oracle's (== OpenCV's, pinned against cv2)."""
+    for k, interp in ((4, 2), (8, 4)):
+        buf = np.empty(1024 * k * k, np.int16)
+        assert N.lib().vr180_debug_weight_table(k, buf.ctypes.data) == 0
+        assert np.array_equal(buf.reshape(1024, k, k), remap_np.weight_table(interp))
+
+
+def test_lowering_matches_golden_ops(golden_maps):
+    """eval(expr) against the PRODUCT classes lowers to exactly the op list the oracle was pinned with."""
+    _, meta = golden_maps
+    for name, case in meta["cases"].items():
+        t = eval(case["expr"], NS)  # noqa: S307 - fixture strings
+        for size_out, size_in, radius in meta["shapes"]:
+            ops = lower_full(t, radius=radius, size_input=tuple(size_in), size_output=tuple(size_out))
+            w, h = size_out
+            want = [("normalize", (w / 2, h / 2), float(min(w, h))), *[tuple(o) for o in case["ops"]],
+                    ("denormalize", (radius, radius), (size_in[1] // 2, size_in[0] // 2))]
+            assert len(ops) == len(want), name
+            for got, exp in zip(ops, want):
+                assert got[0] == exp[0], (name, got, exp)
+                flat = lambda o: np.concatenate([np.atleast_1d(np.asarray(p, dtype=np.float64)).ravel()  # noqa: E731
+                                                 if not isinstance(p, str) else np.array([hash(p) % 997.0]) for p in o[1:]])
+                assert np.allclose(flat(got), flat(exp), rtol=0, atol=1e-15), (name, got, exp)
+            N.make_chain(ops)  # encodable
+
+
+def test_array_api_matches_oracle_on_points(golden_maps):
+    """TransformerBase.transform on arbitrary arrays (points API) agrees with the reference restatement."""
+    _, meta = golden_maps
+    rng = np.random.default_rng(0)
+    x, y = rng.uniform(-0.9, 0.9, (2, 50, 40))
+    for name, case in meta["cases"].items():
+        t = eval(case["expr"], NS)  # noqa: S307
+        with np.errstate(all="ignore"):
+            gx, gy = t.transform(x, y)
+            wx, wy = chain_np.run_chain([tuple(o) for o in case["ops"]], x, y)
+        np.testing.assert_allclose(gx, wx, rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=name)
+        np.testing.assert_allclose(gy, wy, rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=name)
+
+
+def test_equidistant_3d_round_trip():
+    """Reference tests/test_remapper.py:112-115."""
+    x = np.random.rand(101, 100)
+    y = np.random.rand(101, 100)
+    np.testing.assert_allclose(V.equidistant_from_3d(V.equidistant_to_3d(x, y)), (x, y))
+
+
+def test_composition_and_errors():
+    a, b, c = V.ZoomTransformer(2.0), V.EquirectangularEncoder(), V.FisheyeDecoder("equidistant")
+    ab = a * b
+    assert isinstance(ab, V.MultiTransformer) and ab.transformers == [a, b]
+    assert (ab * c).transformers == [a, b, c] and (a * (b * c)).transformers == [a, b, c]
+    assert ((a * b) * (b * c)).transformers == [a, b, b, c]
+    x, y = np.array([[0.1, 0.2]]), np.array([[0.3, -0.1]])
+    with pytest.raises(ValueError, match="Unknown mapping type"):
+        V.FisheyeEncoder("fish").transform(x, y)
+    with pytest.raises(NotImplementedError):
+        V.PolynomialScaler([0, 1]).inverse_transform(x, y)
+    # inverse of the inverse is the forward transform
+    fx, fy = V.FisheyeEncoder("stereographic").transform(x, y)
+    ix, iy = V.FisheyeDecoder("stereographic").inverse_transform(x, y)
+    assert np.array_equal(fx, ix) and np.array_equal(fy, iy)
+    assert repr(V.PolynomialScaler()) == "PolynomialScaler(coefs_reverse=[0, 1])"
+
+
+def test_user_defined_transformer_is_opaque():
+    class Mine(V.PolarRollTransformer):  # README.md:204-219
+        def transform_polar(self, theta, roll, **kwargs):
+            return theta**0.98 + theta**1.01, roll
+
+    t = V.EquirectangularEncoder() * Mine() * V.FisheyeDecoder("equidistant")
+    assert lower_full(t, radius=10.0, size_input=(32, 32), size_output=(16, 16)) is None
+
+    class Tweaked(V.FisheyeEncoder):  # subclass that overrides the math must not be lowered as the parent
+        def transform_polar(self, theta, roll, **kwargs):
+            return theta * 2, roll
+
+    assert Tweaked("equidistant").lower() is None
+    assert V.FisheyeEncoder("equidistant").lower() == [("fisheye_enc", "equidistant")]
+
+
+def test_quaternion_helpers_match_scipy():
+    from scipy.spatial.transform import Rotation
+
+    from vr180_convert_b200.quat import rotation_matrix
+
+    q = V.from_rotation_vector([0.1, 0.2, 0.3])
+    assert np.abs(rotation_matrix(q) - Rotation.from_rotvec([0.1, 0.2, 0.3]).as_matrix()).max() < 1e-15
+    q = V.from_euler_angles(0.3, 0.5, -0.2)
+    assert np.abs(rotation_matrix(q) - Rotation.from_euler("ZYZ", [0.3, 0.5, -0.2]).as_matrix()).max() < 1e-15
+    assert np.abs(rotation_matrix((2.0, 0.2, 0.4, 0.6)) - rotation_matrix((1.0, 0.1, 0.2, 0.3))).max() < 1e-15
+    v = np.random.default_rng(1).normal(size=(7, 3))
+    assert np.allclose(V.rotate_vectors(q, v), v @ rotation_matrix(q).T)
+
+
+def test_shard_range_partitions_frames():
+    for n in (0, 1, 7, 1024, 1025):
+        for ws in (1, 2, 4, 8):
+            parts = [V.shard_range(n, ws, r) for r in range(ws)]
+            flat = [i for p in parts for i in p]
+            assert flat == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= -(-n // ws)
+    with pytest.raises(ValueError):
+        V.shard_range(4, 2, 2)
+
+
+def test_argument_validation_without_gpu():
+    with pytest.raises(ValueError):
+        V.remap_maps(np.zeros((4, 4, 3), np.uint8), np.zeros((2, 2), np.float32), np.zeros((2, 2), np.float32),
+                     interpolation=7)
+    with pytest.raises(NotImplementedError):
+        V.remap_maps(np.zeros((4, 4, 3), np.uint8), np.zeros((2, 2), np.float32), np.zeros((2, 2), np.float32),
+                     border_mode=5)
+    with pytest.raises(ValueError):
+        N.make_chain([("poly", list(range(13)))])
+    with pytest.raises(ValueError):
+        N.make_chain([])
+    # C-side validation: NULL / bad sizes are rejected before any CUDA call
+    handle = N.lib()
+    assert handle.vr180_build_map(None, 4, 4, None, None, 4, None) == -1
+    assert handle.vr180_remap(None, None) == -1
+    assert handle.vr180_ctx_run(None, None) == -1

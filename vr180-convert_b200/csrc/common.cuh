@@ -1,0 +1,64 @@
+// common.cuh -- host-side helpers shared by the translation units of libvr180_b200.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/vr180_b200.h"
+
+namespace vr180 {
+
+extern std::atomic<uint64_t> g_launches;
+void set_cuda_error(cudaError_t e, const char* where);
+
+#define VR180_CUDA(call)                                  \
+    do {                                                  \
+        cudaError_t e__ = (call);                         \
+        if (e__ != cudaSuccess) {                         \
+            ::vr180::set_cuda_error(e__, #call);          \
+            return VR180_ERR_CUDA;                        \
+        }                                                 \
+    } while (0)
+
+// Select the device that owns `ptr` for the duration of a call (this library links its own static cudart, whose
+// current-device state is independent of the caller's).
+struct DeviceGuard {
+    int prev = -1;
+    int dev = -1;
+    bool ok = false;
+    explicit DeviceGuard(const void* ptr) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess || a.type != cudaMemoryTypeDevice) {
+            cudaGetLastError();
+            return;
+        }
+        dev = a.device;
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) return;
+        ok = true;
+    }
+    explicit DeviceGuard(int device) {
+        dev = device;
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) return;
+        ok = true;
+    }
+    ~DeviceGuard() {
+        if (ok && prev != dev && prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// internal launchers (kernels.cu); the device is already selected by the caller
+int launch_build_map(const vr180_chain_t* chain, int out_w, int out_h, float* xmap, float* ymap, int64_t pitch,
+                     cudaStream_t st);
+int launch_pack_lut(const float* xmap, const float* ymap, int64_t map_pitch, int out_w, int out_h, int32_t* fixed,
+                    int64_t fixed_pitch, cudaStream_t st);
+int launch_remap(const vr180_remap_params_t* p, cudaStream_t st);
+int launch_get_radius(const vr180_image_t* views, int n_views, int n_frames, double threshold, int32_t* transitions,
+                      double* radius, cudaStream_t st);
+int validate_chain(const vr180_chain_t* c);
+
+}  // namespace vr180

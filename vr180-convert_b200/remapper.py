@@ -1,0 +1,392 @@
+"""`get_map`, `get_radius_smart`, `apply`, `apply_lr` with the reference's signatures
+(/root/reference/src/vr180_convert/remapper.py:23-90, 324-520), executed by libvr180_b200.so.
+
+NumPy arrays in, NumPy arrays out; the arithmetic (chain evaluation, OpenCV-exact sampling, radius scan, SBS
+packing) happens in CUDA kernels through the C ABI.  There is no CPU fallback: without the shared object or a
+CUDA device these functions raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from logging import getLogger
+from pathlib import Path
+from typing import Any, Literal, Sequence
+
+import numpy as np
+from numpy.typing import NDArray
+
+from . import _native as N
+from .transformer import DenormalizeTransformer, NormalizeTransformer, TransformerBase
+
+LOG = getLogger(__name__)
+
+# OpenCV's integer constants are the reference's API (remapper.py:330-331; cli.py:57-79 resolves names via getattr(cv, ...))
+INTER_NEAREST, INTER_LINEAR, INTER_CUBIC, INTER_AREA, INTER_LANCZOS4 = 0, 1, 2, 3, 4
+BORDER_CONSTANT, BORDER_REPLICATE, BORDER_REFLECT, BORDER_WRAP, BORDER_REFLECT_101, BORDER_TRANSPARENT = 0, 1, 2, 3, 4, 5
+
+_ctx_lock = threading.Lock()
+_ctxs: dict[int, C.c_void_p] = {}
+_default_device = 0
+
+
+def set_device(device: int) -> None:
+    """CUDA device used by the NumPy-level API of this process (one process per GPU)."""
+    global _default_device
+    _default_device = int(device)
+
+
+def _ctx(device: int | None = None) -> C.c_void_p:
+    dev = _default_device if device is None else int(device)
+    with _ctx_lock:
+        if dev not in _ctxs:
+            handle = C.c_void_p()
+            N.check(N.lib().vr180_ctx_create(dev, C.byref(handle)), "vr180_ctx_create")
+            _ctxs[dev] = handle
+        return _ctxs[dev]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# lowering helpers
+# ---------------------------------------------------------------------------------------------------------
+def full_chain(transformer: TransformerBase, *, radius: float, size_input: tuple[int, int]) -> TransformerBase:
+    """Normalize * t * Denormalize(scale=(r, r), center=(cols//2, rows//2)) -- remapper.py:51-57."""
+    return (NormalizeTransformer() * transformer
+            * DenormalizeTransformer(scale=(radius, radius), center=(size_input[1] // 2, size_input[0] // 2)))
+
+
+def lower_full(transformer: TransformerBase, *, radius: float, size_input: tuple[int, int],
+               size_output: tuple[int, int]) -> "list[tuple] | None":
+    ops = full_chain(transformer, radius=radius, size_input=size_input).lower(
+        shape=(size_output[1], size_output[0]), inverse=False)
+    if ops is None or len(ops) > N.MAX_OPS:
+        return None
+    return ops
+
+
+def host_maps(transformer: TransformerBase, *, radius: float, size_input: tuple[int, int],
+              size_output: tuple[int, int]) -> tuple[NDArray[np.float32], NDArray[np.float32]]:
+    """Opaque (user-defined) transformers: run THEIR NumPy code once on the pixel grid (remapper.py:50-58)."""
+    xmap, ymap = np.meshgrid(np.arange(size_output[0]), np.arange(size_output[1]))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        xmap, ymap = full_chain(transformer, radius=radius, size_input=size_input).transform(xmap, ymap)
+    return np.ascontiguousarray(xmap, dtype=np.float32), np.ascontiguousarray(ymap, dtype=np.float32)
+
+
+def get_map(
+    transformer: TransformerBase,
+    *,
+    radius: float,
+    size_input: tuple[int, int],
+    size_output: tuple[int, int] = (2048, 2048),
+) -> tuple[NDArray[np.float32], NDArray[np.float32]]:
+    """float32 (H, W) source-coordinate maps for cv2.remap-style sampling (remapper.py:23-59).
+
+    Recognised transformer chains are evaluated per pixel in float64 by csrc/kernels.cu:k_build_map and rounded
+    once to float32; chains containing user-defined Python transformers are evaluated by that Python code."""
+    ops = lower_full(transformer, radius=radius, size_input=size_input, size_output=size_output)
+    if ops is None:
+        return host_maps(transformer, radius=radius, size_input=size_input, size_output=size_output)
+    import torch
+
+    w, h = int(size_output[0]), int(size_output[1])
+    dev = torch.device("cuda", _default_device)
+    maps = torch.empty((2, h, w), dtype=torch.float32, device=dev)
+    chain = N.make_chain(ops)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    N.check(N.lib().vr180_build_map(C.byref(chain), w, h, maps[0].data_ptr(), maps[1].data_ptr(), w, stream),
+            "vr180_build_map")
+    out = maps.cpu().numpy()
+    return out[0], out[1]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# radius
+# ---------------------------------------------------------------------------------------------------------
+def _centre_line(img: NDArray) -> NDArray:
+    """The one row / column get_radius reads (transformer.py:125-129), as a (1, n, C) or (n, 1, C) uint8 image
+    whose centre line is that row / column again -- so only ~n*C bytes are uploaded."""
+    if img.ndim != 3:
+        raise IndexError("too many indices for array: get_radius needs an (H, W, C) image")
+    height, width = img.shape[:2]
+    if width > height:
+        return np.ascontiguousarray(img[height // 2: height // 2 + 1, :, :])
+    return np.ascontiguousarray(img[:, width // 2: width // 2 + 1, :])
+
+
+def _device_radius(images: Sequence[NDArray], threshold: float = 10) -> list[float]:
+    import torch
+
+    dev = torch.device("cuda", _default_device)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    out: list[float] = []
+    for img in images:
+        line = _centre_line(np.asarray(img))
+        if line.dtype != np.uint8:
+            raise TypeError("get_radius kernel takes uint8 images")
+        rows, cols, ch = line.shape
+        if ch > 4:
+            raise ValueError("get_radius kernel supports up to 4 channels")
+        # keep the reference's row-vs-column decision: a 1 x n line has cols > rows unless n == 1
+        if cols <= rows and rows == 1:
+            raise IndexError("index 0 is out of bounds for axis 0 with size 0")
+        d_line = torch.from_numpy(line).to(dev)
+        trans = torch.empty(2, dtype=torch.int32, device=dev)
+        im = N.Image(d_line.data_ptr(), rows, cols, ch, 0, cols * ch, rows * cols * ch)
+        N.check(N.lib().vr180_get_radius(C.byref(im), 1, 1, float(threshold), trans.data_ptr(), None, stream),
+                "vr180_get_radius")
+        first, last = (int(v) for v in trans.cpu())
+        if first < 0 or last < 0:
+            raise IndexError("index 0 is out of bounds for axis 0 with size 0")  # np.where(...)[0][0] on empty
+        out.append((last - first) / 2)
+    return out
+
+
+def get_radius_smart(radius: float | Literal["auto", "max"], images: Sequence[NDArray]) -> float:
+    """remapper.py:62-90."""
+    if isinstance(radius, str) and radius == "auto":
+        radius_ = max(_device_radius(images))
+    elif isinstance(radius, str) and radius == "max":
+        radius_ = min(images[0].shape[0] / 2, images[0].shape[1] / 2)
+    else:
+        radius_ = radius
+    LOG.info(f"Radius: {radius_}, strategy: {radius}, image shape: {images[0].shape}")
+    return radius_
+
+
+# ---------------------------------------------------------------------------------------------------------
+# apply / apply_lr
+# ---------------------------------------------------------------------------------------------------------
+def _border_bytes(value: Any, channels: int) -> tuple[int, int, int, int]:
+    """cv2 converts a Python scalar to Scalar(v, 0, 0, 0) and saturates each entry to uint8."""
+    vals = [float(value), 0.0, 0.0, 0.0] if np.isscalar(value) else [*map(float, value), 0.0, 0.0, 0.0, 0.0][:4]
+    return tuple(int(min(255, max(0, np.rint(v)))) for v in vals)  # type: ignore[return-value]
+
+
+def _check_modes(interpolation: int, border_mode: int) -> tuple[int, int]:
+    interpolation = int(interpolation)
+    if interpolation == INTER_AREA:  # cv::remap treats INTER_AREA as INTER_LINEAR
+        interpolation = INTER_LINEAR
+    if interpolation not in (INTER_NEAREST, INTER_LINEAR, INTER_CUBIC, INTER_LANCZOS4):
+        raise ValueError(f"Unknown interpolation method {interpolation}")
+    border_mode = int(border_mode)
+    if border_mode == BORDER_TRANSPARENT:
+        raise NotImplementedError("BORDER_TRANSPARENT leaves uninitialised memory in the reference; not supported")
+    if border_mode not in (BORDER_CONSTANT, BORDER_REPLICATE, BORDER_REFLECT, BORDER_WRAP, BORDER_REFLECT_101):
+        raise ValueError(f"Unknown/unsupported border type {border_mode}")
+    return interpolation, border_mode
+
+
+def _as_image(a: Any) -> NDArray:
+    img = np.asarray(a)
+    if img.dtype != np.uint8:
+        raise TypeError("the B200 remap path takes uint8 images (what cv.imread returns)")
+    if img.ndim == 2:
+        img = img[:, :, None]
+    if img.ndim != 3 or img.shape[2] not in (1, 3, 4):
+        raise ValueError(f"unsupported image shape {img.shape}")
+    if img.strides[2] != 1 or img.strides[1] != img.shape[2] or img.strides[0] < img.shape[1] * img.shape[2]:
+        img = np.ascontiguousarray(img)  # only pixel-contiguous rows can be described by a pitch
+    return img
+
+
+def warp_host(
+    transformers: Sequence[TransformerBase],
+    images: Sequence[NDArray],
+    *,
+    radii: Sequence[float],
+    share_map: bool,
+    size_output: tuple[int, int],
+    interpolation: int,
+    border_mode: int,
+    border_value: Any,
+) -> NDArray[np.uint8]:
+    """One host job: 1 or 2 views (eyes) of equal geometry -> one (H, n_views*W, C) frame (views side by side)."""
+    lib = N.lib()
+    views = [_as_image(im) for im in images]
+    rows, cols, ch = views[0].shape
+    for v in views[1:]:
+        if v.shape != views[0].shape:
+            raise ValueError("left and right images must have the same shape")
+    w, h = int(size_output[0]), int(size_output[1])
+    n_views = len(views)
+    squeeze = np.asarray(images[0]).ndim == 2
+    dst = np.empty((h, w * n_views, ch), dtype=np.uint8)
+
+    job = N.HostJob()
+    job.n_views, job.n_frames = n_views, 1
+    job.src_rows, job.src_cols, job.channels = rows, cols, ch
+    keep: list[Any] = []
+    n_maps = 1 if (share_map or n_views == 1) else n_views
+    lowered = [lower_full(transformers[m], radius=radii[m], size_input=(rows, cols), size_output=(w, h))
+               for m in range(n_maps)]
+    analytic = all(o is not None for o in lowered)
+    job.map_kind = N.MAPSRC_ANALYTIC if analytic else N.MAPSRC_FLOAT2
+    job.share_map = 1 if (share_map and n_views == 2) else 0
+    for m in range(n_maps):
+        if analytic:
+            chain = N.make_chain(lowered[m])
+            keep.append(chain)
+            job.chain[m] = C.pointer(chain)
+        else:
+            xm, ym = (get_map if lowered[m] is not None else host_maps)(
+                transformers[m], radius=radii[m], size_input=(rows, cols), size_output=(w, h))
+            xm, ym = np.ascontiguousarray(xm), np.ascontiguousarray(ym)
+            keep += [xm, ym]
+            job.xmap[m], job.ymap[m] = xm.ctypes.data, ym.ctypes.data
+    for v, img in enumerate(views):
+        job.src[v] = img.ctypes.data
+        job.src_pitch[v] = img.strides[0]
+        job.src_frame_stride[v] = img.strides[0] * rows
+    job.out_w, job.out_h = w, h
+    job.interpolation, job.border_mode = interpolation, border_mode
+    for i, b in enumerate(_border_bytes(border_value, ch)):
+        job.border_value[i] = b
+    job.dst = dst.ctypes.data
+    job.dst_pitch = dst.strides[0]
+    job.dst_frame_stride = dst.strides[0] * h
+    N.check(lib.vr180_ctx_run(_ctx(), C.byref(job)), "vr180_ctx_run")
+    del keep
+    return dst[:, :, 0] if squeeze else dst
+
+
+def _imread(path: Any) -> NDArray:
+    import cv2 as cv  # file decode only (out of the hot path)
+
+    return cv.imread(Path(path).as_posix())
+
+
+def _imwrite(path: Any, image: NDArray) -> None:
+    import cv2 as cv
+
+    cv.imwrite(Path(path).as_posix(), image)
+
+
+def apply(
+    transformer: TransformerBase,
+    *,
+    in_paths: Sequence[Path | str | NDArray] | Path | str | NDArray,
+    out_paths: Sequence[Path | str] | None | Path | str = None,
+    size_output: tuple[int, int] = (2048, 2048),
+    interpolation: int = INTER_LANCZOS4,
+    boarder_mode: int = BORDER_CONSTANT,
+    boarder_value: int | tuple[int, int, int] = 0,
+    radius: float | Literal["auto", "max"] = "auto",
+) -> Sequence[NDArray[np.uint8]]:
+    """Remap every input image with ONE map built from images[0]'s shape (remapper.py:324-403).
+    Argument names (including the `boarder_*` spelling) are the reference's."""
+    in_list = [in_paths] if isinstance(in_paths, (str, Path, np.ndarray)) else list(in_paths)
+    out_list = [out_paths] if isinstance(out_paths, (str, Path)) else out_paths
+    interpolation, border_mode = _check_modes(interpolation, boarder_mode)
+
+    images = [_imread(p) if isinstance(p, (str, Path)) else p for p in in_list]
+    radius_ = get_radius_smart(radius, images)
+    size_in = (images[0].shape[0], images[0].shape[1])
+    results = []
+    for img in images:
+        if np.asarray(img).shape[:2] != size_in:
+            # the reference samples a differently-sized image with images[0]'s map; keep that behaviour
+            LOG.warning("image shape %s differs from the first image %s; using the first image's map",
+                        np.asarray(img).shape, size_in)
+        results.append(_warp_with_first_geometry(transformer, img, size_in, radius_, size_output, interpolation,
+                                                 border_mode, boarder_value))
+    if out_list is not None:
+        for to_path, image in zip(out_list, results):
+            _imwrite(to_path, image)
+    return results
+
+
+def _warp_with_first_geometry(transformer, img, size_in, radius_, size_output, interpolation, border_mode, border_value):
+    img = np.asarray(img)
+    if img.shape[:2] == size_in:
+        return warp_host([transformer], [img], radii=[radius_], share_map=True, size_output=size_output,
+                         interpolation=interpolation, border_mode=border_mode, border_value=border_value)
+    # map geometry (centre, radius) comes from the first image, sampling bounds from this one: FLOAT2 route
+    xm, ym = get_map(transformer, radius=radius_, size_input=size_in, size_output=size_output)
+    return remap_maps(img, xm, ym, interpolation=interpolation, border_mode=border_mode, border_value=border_value)
+
+
+def remap_maps(img: NDArray, xmap: NDArray, ymap: NDArray, *, interpolation: int = INTER_LINEAR,
+               border_mode: int = BORDER_CONSTANT, border_value: Any = 0) -> NDArray[np.uint8]:
+    """cv2.remap(img, xmap, ymap, interpolation, borderMode, borderValue) for uint8 images and float32 maps."""
+    interpolation, border_mode = _check_modes(interpolation, border_mode)
+    xm = np.ascontiguousarray(xmap, dtype=np.float32)
+    ym = np.ascontiguousarray(ymap, dtype=np.float32)
+    if xm.shape != ym.shape or xm.ndim != 2:
+        raise ValueError("xmap / ymap must be 2-D float32 arrays of equal shape")
+    view = _as_image(img)
+    rows, cols, ch = view.shape
+    h, w = xm.shape
+    dst = np.empty((h, w, ch), dtype=np.uint8)
+    job = N.HostJob()
+    job.n_views = job.n_frames = 1
+    job.src[0] = view.ctypes.data
+    job.src_rows, job.src_cols, job.channels = rows, cols, ch
+    job.src_pitch[0] = view.strides[0]
+    job.src_frame_stride[0] = view.strides[0] * rows
+    job.map_kind = N.MAPSRC_FLOAT2
+    job.xmap[0], job.ymap[0] = xm.ctypes.data, ym.ctypes.data
+    job.out_w, job.out_h = w, h
+    job.interpolation, job.border_mode = interpolation, border_mode
+    for i, b in enumerate(_border_bytes(border_value, ch)):
+        job.border_value[i] = b
+    job.dst, job.dst_pitch, job.dst_frame_stride = dst.ctypes.data, dst.strides[0], dst.strides[0] * h
+    N.check(N.lib().vr180_ctx_run(_ctx(), C.byref(job)), "vr180_ctx_run")
+    return dst[:, :, 0] if np.asarray(img).ndim == 2 else dst
+
+
+def _anaglyph(images: Sequence[NDArray]) -> NDArray:
+    """`merge=True` branch of apply_lr (remapper.py:485-516): float64 channel-mean tint + "L"/"R" labels.
+    Calibration aid outside the hot path; host NumPy, cv2 only for putText."""
+    import cv2 as cv
+
+    colors = [(0, 128, 255), (255, 128, 0)]
+    combine = sum(np.mean(im, axis=-1)[..., None] * np.array(col).reshape([1] * (im.ndim - 1) + [3])
+                  for im, col in zip(images, colors))
+    combine = combine / 255
+    cv.putText(combine, "L", (0, len(combine[1]) // 10), cv.FONT_HERSHEY_SIMPLEX, len(combine) // 1000, colors[0], 2,
+               cv.LINE_AA)
+    cv.putText(combine, "R", (len(combine[1]) // 2, len(combine[0]) // 10), cv.FONT_HERSHEY_SIMPLEX,
+               len(combine) // 1000, colors[1], 2, cv.LINE_AA)
+    return combine
+
+
+def apply_lr(
+    transformer: TransformerBase | tuple[TransformerBase, TransformerBase],
+    *,
+    left_path: Path | str | NDArray,
+    right_path: Path | str | NDArray,
+    out_path: Path | str,
+    size_output: tuple[int, int] = (2048, 2048),
+    interpolation: int = INTER_LANCZOS4,
+    boarder_mode: int = BORDER_CONSTANT,
+    boarder_value: int | tuple[int, int, int] = 0,
+    radius: float | Literal["auto", "max"] = "auto",
+    merge: bool = False,
+) -> None:
+    """Stereo pair -> side-by-side frame written to `out_path` (remapper.py:406-520).  Both eyes are warped by
+    one kernel launch that writes each eye into its half of the SBS frame (no separate concatenate)."""
+    sbs = lr_frame(transformer, left_path, right_path, size_output=size_output, interpolation=interpolation,
+                   boarder_mode=boarder_mode, boarder_value=boarder_value, radius=radius)
+    if merge:
+        w = int(size_output[0])
+        sbs = _anaglyph([sbs[:, :w], sbs[:, w:]])
+    _imwrite(out_path, sbs)
+    LOG.info(f"Saved to {Path(out_path).absolute()}")
+
+
+def lr_frame(transformer, left, right, *, size_output=(2048, 2048), interpolation=INTER_LANCZOS4,
+             boarder_mode=BORDER_CONSTANT, boarder_value=0, radius="auto") -> NDArray[np.uint8]:
+    """The in-memory part of apply_lr: returns the (H, 2W, C) SBS frame."""
+    interpolation, border_mode = _check_modes(interpolation, boarder_mode)
+    if isinstance(left, (str, Path)) and isinstance(right, (str, Path)) and left == right:
+        image = _imread(left)  # one SBS source file: split into halves (views, not copies) -- remapper.py:448-456
+        left, right = image[:, : image.shape[1] // 2], image[:, image.shape[1] // 2:]
+    eyes = [_imread(p) if isinstance(p, (str, Path)) else p for p in (left, right)]
+    if isinstance(transformer, tuple):  # per-eye transformer: own radius and own map per eye (remapper.py:460-473)
+        radii = [get_radius_smart(radius, [eye]) for eye in eyes]
+        return warp_host(list(transformer), eyes, radii=radii, share_map=False, size_output=size_output,
+                         interpolation=interpolation, border_mode=border_mode, border_value=boarder_value)
+    radius_ = get_radius_smart(radius, eyes)  # one radius = max over both eyes, ONE map (remapper.py:475-484)
+    return warp_host([transformer], eyes, radii=[radius_], share_map=True, size_output=size_output,
+                     interpolation=interpolation, border_mode=border_mode, border_value=boarder_value)
