@@ -1,0 +1,507 @@
+#!/usr/bin/env python
+"""bench.py -- SBS equirect output Mpix/s of the reprojection hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic stereo pairs.  Default workload (the
+configuration BASELINE.json's target is quoted on -- "bit-exact INTER_LINEAR SBS equirectangular output ... on
+batched 8K stereo frames"): B pairs of 2 x 4096^2 fisheye frames -> B x (8192 x 4096) SBS frames, per-eye
+Euclidean3DRotator + PolynomialScaler chain (configs[2]), fused analytic warp, INTER_LINEAR.
+
+  value      whole-job Mpix/s with the frames resident in HBM (CUDA events on the launch stream, max over ranks)
+  e2e        the same metric through the C-ABI host call the NumPy API uses (vr180_ctx_run) with pinned HOST
+             buffers: H2D of every source frame and D2H of every SBS frame inside the timed region
+  roofline   algorithmic bytes of one launch / its measured duration vs the measured HBM copy bandwidth
+  cpu_baseline / --impl reference
+             the reference's CPU path (NumPy chain restated in oracle/chain_np.py + the real cv2.remap +
+             np.concatenate) on this box's host cores, on a bounded sample of the same workload
+
+N > 1: one process per GPU (torchrun or self-spawned), frames sharded statically, no data-path collective
+(weak scaling: every rank warps its own B pairs); torch.distributed is used only for the barrier and the
+max-over-ranks of the device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import socket
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+Q_HALF = (0.9999093510664558, 0.00500054686470522, 0.01000109372941044, -0.00750082029705783)
+POLY = [0, 1, -0.02, 0.003]
+
+WORKLOADS = {
+    # name: (per-eye input n, output n, interpolation, per_eye_tuple, map_source, radius, default pairs per step)
+    "8k_rot_poly_linear": dict(n=4096, interp=1, tuple_=True, chain="rot_poly", src="analytic", radius="fixed", pairs=16,
+                               desc="batched 8K stereo pairs (2x4096^2 -> 8192x4096), per-eye Euclidean3DRotator+"
+                                    "PolynomialScaler, fused analytic warp, INTER_LINEAR [BASELINE configs[2], batched]"),
+    "4k_pair_linear": dict(n=2048, interp=1, tuple_=False, chain="base", src="analytic", radius="fixed", pairs=1,
+                           desc="single 4K pair (2x2048^2 -> 4096x2048), base chain, fused analytic, INTER_LINEAR "
+                                "[BASELINE configs[1]]; a ring of pairs larger than L2 is cycled"),
+    "5k7_lut_linear": dict(n=2880, interp=1, tuple_=False, chain="base", src="lut_fixed", radius="fixed", pairs=32,
+                           desc="batched 5.7K pairs (2x2880^2 -> 5760x2880), cached fixed-point LUT, INTER_LINEAR "
+                                "[BASELINE configs[3]]"),
+    "8k_cubic_auto": dict(n=4096, interp=2, tuple_=False, chain="base", src="analytic", radius="auto", pairs=16,
+                          desc="batched 8K pairs, base chain, fused analytic + get_radius per frame consumed on device, "
+                               "INTER_CUBIC [BASELINE configs[4]]"),
+}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------------------
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons, power = [], [], set(), []
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def build_transformers(V, kind: str, tuple_: bool):
+    enc, dec = V.EquirectangularEncoder(), V.FisheyeDecoder("equidistant")
+    if kind == "base":
+        return enc * dec
+    ql = V.quaternion(*Q_HALF)
+    qr = ql.conj()  # cli.py:312-319: left eye gets conj(half_q), right eye half_q
+    tl = enc * V.Euclidean3DRotator(qr) * V.PolynomialScaler(POLY) * dec
+    tr = enc * V.Euclidean3DRotator(ql) * V.PolynomialScaler(POLY) * dec
+    return (tl, tr) if tuple_ else tl
+
+
+def oracle_ops(kind: str, conj: bool):
+    from oracle import chain_np
+
+    if kind == "base":
+        return [("equirect_enc", True), ("fisheye_dec", "equidistant")]
+    w, x, y, z = Q_HALF
+    if conj:
+        x, y, z = -x, -y, -z
+    return [("equirect_enc", True), ("rot3", chain_np.quat_to_matrix(w, x, y, z).ravel().tolist()), ("poly", POLY),
+            ("fisheye_dec", "equidistant")]
+
+
+def synth_frames_torch(torch, n_frames: int, n: int, seed: int, device):
+    """Synthetic fisheye frames: uniform random bytes inside the disc, zeros outside."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    frames = torch.randint(0, 256, (n_frames, n, n, 3), dtype=torch.uint8, device=device, generator=g)
+    yy = torch.arange(n, device=device).view(n, 1)
+    xx = torch.arange(n, device=device).view(1, n)
+    outside = ((xx - n // 2) ** 2 + (yy - n // 2) ** 2) > (n // 2 - 8) ** 2
+    frames[:, outside] = 0
+    return frames
+
+
+def touched_fraction(torch, maps, n_in: int, taps: int) -> float:
+    """Unique source pixels touched by the interpolation footprint / source pixels (algorithmic input bytes)."""
+    xm, ym = maps[0].reshape(-1), maps[1].reshape(-1)
+    ok = torch.isfinite(xm) & torch.isfinite(ym)
+    sx = torch.round(xm[ok].double() * 32).long() >> 5
+    sy = torch.round(ym[ok].double() * 32).long() >> 5
+    touched = torch.zeros(n_in * n_in, dtype=torch.bool, device=maps.device)
+    lo, hi = -(taps // 2 - 1), taps // 2
+    for dy in range(lo, hi + 1):
+        for dx in range(lo, hi + 1):
+            x, y = sx + dx, sy + dy
+            m = (x >= 0) & (x < n_in) & (y >= 0) & (y < n_in)
+            touched[(y[m] * n_in + x[m])] = True
+    return float(touched.float().mean().item())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU reference path (oracle port: NumPy chain restatement + the real cv2.remap + concatenate)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_setup(wl: dict, sample_pairs: int):
+    import cv2
+
+    from oracle import chain_np
+
+    n = wl["n"]
+    rng_frames = []
+    yy, xx = np.ogrid[:n, :n]
+    outside = (xx - n // 2) ** 2 + (yy - n // 2) ** 2 > (n // 2 - 8) ** 2
+    for i in range(2 * sample_pairs):
+        img = np.random.default_rng(i).integers(0, 256, (n, n, 3), dtype=np.uint8)
+        img[outside] = 0
+        rng_frames.append(img)
+    t0 = time.perf_counter()
+    n_maps = 2 if wl["tuple_"] else 1
+    maps = [chain_np.get_map(oracle_ops(wl["chain"], conj=(m == 0 and wl["tuple_"])), radius=n / 2, size_input=(n, n),
+                             size_output=(n, n)) for m in range(n_maps)]
+    t_maps = time.perf_counter() - t0
+    interp = {1: cv2.INTER_LINEAR, 2: cv2.INTER_CUBIC}[wl["interp"]]
+
+    def step():
+        for p in range(sample_pairs):
+            eyes = []
+            for e in range(2):
+                img = rng_frames[2 * p + e]
+                if wl["radius"] == "auto":
+                    chain_np.get_radius(img)
+                xm, ym = maps[e if n_maps == 2 else 0]
+                eyes.append(cv2.remap(img, xm, ym, interpolation=interp, borderMode=cv2.BORDER_CONSTANT, borderValue=0))
+            np.concatenate(eyes, axis=1)
+
+    return step, t_maps, cv2.getNumThreads()
+
+
+def run_reference(args, wl_name: str, wl: dict) -> dict:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return {}
+    n = wl["n"]
+    sample_pairs = 2 if n >= 4096 else 4
+    step, t_maps, threads = cpu_reference_setup(wl, sample_pairs)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    mpix = sample_pairs * n * 2 * n / 1e6
+    value = mpix / dt
+    pairs = wl["pairs"]
+    incl = pairs * n * 2 * n / 1e6 / (t_maps + pairs * dt / sample_pairs)
+    return {
+        "impl": "reference", "metric": "SBS equirect output Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 maps / u8 fixed-point sampling", "data": "synthetic",
+        "config": {"workload": wl_name, "description": wl["desc"], "sample_pairs_per_step": sample_pairs},
+        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": os.cpu_count(), "kind": "port",
+                         "cv2_threads": threads,
+                         "sample": f"{sample_pairs} pairs per step: cv2.remap x2 + np.concatenate with the maps cached "
+                                   f"(reference apply(): one get_map for N images); get_map itself took {t_maps:.2f} s "
+                                   f"for {2 if wl['tuple_'] else 1} map(s), single-threaded NumPy",
+                         "map_build_s": t_maps, "value_incl_map_build_for_step_batch": incl},
+        "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def time_device(torch, fn, steps: int, warmup: int, dist):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        fn()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        from vr180_convert_b200.shard import max_over_ranks
+
+        ms = max_over_ranks(ms, dist, device="cuda")
+        dist.barrier()
+    return ms / steps
+
+
+def run_workload(torch, V, wl_name: str, wl: dict, steps: int, warmup: int, dist, pairs: int | None = None,
+                 want_e2e: bool = True, device=None):
+    n = wl["n"]
+    pairs = pairs or wl["pairs"]
+    ring = 1
+    if pairs * n * n * 3 * 4 < 300e6:  # keep the working set of consecutive steps above the 126 MB L2
+        ring = int(np.ceil(300e6 / (pairs * n * n * 3 * 4)))
+    t = build_transformers(V, wl["chain"], wl["tuple_"])
+    radius = "auto" if wl["radius"] == "auto" else n / 2
+    wp = V.SbsWarper(t, size_input=(n, n), size_output=(n, n), interpolation=wl["interp"], radius=radius,
+                     map_source=wl["src"], device=device)
+    left = synth_frames_torch(torch, pairs * ring, n, 1, device)
+    right = synth_frames_torch(torch, pairs * ring, n, 2, device)
+    out = torch.empty((pairs * ring, n, 2 * n, 3), dtype=torch.uint8, device=device)
+    if wl["src"] != "analytic":
+        wp.fixed_lut() if wl["src"] == "lut_fixed" else wp.maps()
+    state = {"i": 0}
+
+    def step():
+        k = state["i"] % ring
+        state["i"] += 1
+        s = slice(k * pairs, (k + 1) * pairs)
+        wp(left[s], right[s], out=out[s])
+
+    lib = V._native.lib()
+    l0 = lib.vr180_launch_count()
+    step()
+    launches_per_step = lib.vr180_launch_count() - l0
+    ms = time_device(torch, step, steps, warmup, dist)
+    mpix_step = pairs * n * 2 * n / 1e6
+
+    # algorithmic bytes (DESIGN.md "roofline"): output written once + unique source pixels touched, per eye
+    taps = {0: 2, 1: 2, 2: 4, 4: 8}[wl["interp"]]
+    plan_for_maps = wp if not wp.auto_radius else V.SbsWarper(t, size_input=(n, n), size_output=(n, n),
+                                                              interpolation=wl["interp"], radius=-(n // 2 - 8) - 0.5,
+                                                              map_source="lut", device=device)
+    maps = plan_for_maps.maps()
+    fracs = [touched_fraction(torch, maps[m], n, taps) for m in range(maps.shape[0])]
+    frac_in = sum(fracs) / len(fracs)
+    if plan_for_maps is not wp or wl["src"] == "analytic":
+        plan_for_maps._maps = None
+    del maps
+    lut_bytes = {"analytic": 0, "lut": 8, "lut_fixed": 8}[wl["src"]] * n * n * (1 if not wl["tuple_"] else 2)
+    bytes_step = pairs * (2 * n * n * 3 + 2 * frac_in * n * n * 3) + lut_bytes  # LUT is read once per launch
+    res = {"ms_per_step": ms, "mpix_per_step": mpix_step, "value": mpix_step / (ms / 1e3), "pairs": pairs,
+           "launches_per_step": launches_per_step, "bytes_per_step": bytes_step, "touched_fraction": frac_in,
+           "ring": ring}
+
+    if want_e2e:
+        import ctypes as C
+
+        N = V._native
+        pe = min(pairs, 8)
+        nbytes_in, nbytes_out = pe * n * n * 3, pe * n * 2 * n * 3
+        ptrs = []
+        for nb in (nbytes_in, nbytes_in, nbytes_out):
+            p = C.c_void_p()
+            N.check(lib.vr180_host_alloc(nb, C.byref(p)), "vr180_host_alloc")
+            ptrs.append(p)
+        h_l = np.ctypeslib.as_array(C.cast(ptrs[0], C.POINTER(C.c_uint8)), shape=(pe, n, n, 3))
+        h_r = np.ctypeslib.as_array(C.cast(ptrs[1], C.POINTER(C.c_uint8)), shape=(pe, n, n, 3))
+        h_o = np.ctypeslib.as_array(C.cast(ptrs[2], C.POINTER(C.c_uint8)), shape=(pe, n, 2 * n, 3))
+        h_l[:] = left[:pe].cpu().numpy()
+        h_r[:] = right[:pe].cpu().numpy()
+        job = N.HostJob()
+        job.n_views, job.n_frames = 2, pe
+        job.src[0], job.src[1] = ptrs[0].value, ptrs[1].value
+        job.src_rows, job.src_cols, job.channels = n, n, 3
+        for v in range(2):
+            job.src_pitch[v], job.src_frame_stride[v] = n * 3, n * n * 3
+        keep = []
+        if wl["src"] == "analytic":
+            job.map_kind = N.MAPSRC_ANALYTIC
+            for m, ch in enumerate(wp._chains):
+                job.chain[m] = C.pointer(ch)
+        else:
+            job.map_kind = N.MAPSRC_FLOAT2
+            hm = wp.maps().cpu().numpy()
+            keep.append(hm)
+            for m in range(hm.shape[0]):
+                job.xmap[m], job.ymap[m] = hm[m, 0].ctypes.data, hm[m, 1].ctypes.data
+            job.maps_cache_key = 1
+        job.share_map = 1 if wp.share_map else 0
+        job.radius_mode = 1 if wp.auto_radius else 0
+        job.threshold = 10.0
+        job.out_w = job.out_h = n
+        job.interpolation, job.border_mode = wl["interp"], 0
+        job.dst, job.dst_pitch, job.dst_frame_stride = ptrs[2].value, 2 * n * 3, n * 2 * n * 3
+        handle = C.c_void_p()
+        N.check(lib.vr180_ctx_create(torch.cuda.current_device(), C.byref(handle)), "ctx_create")
+
+        def e2e_step():
+            N.check(lib.vr180_ctx_run(handle, C.byref(job)), "vr180_ctx_run")
+
+        for _ in range(2):
+            e2e_step()
+        if dist is not None:
+            dist.barrier()
+        e_steps = max(3, min(steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()  # synchronous: returns when every SBS frame is in host memory
+        dt = (time.perf_counter() - t0) / e_steps
+        if dist is not None:
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        # spot check: the host path produced the same frame as the device-resident path
+        same = bool(np.array_equal(h_o[0], out[0].cpu().numpy())) if ring == 1 or True else True
+        res["e2e"] = {"value": pe * n * 2 * n / 1e6 / dt, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * nbytes_in,
+                      "d2h_bytes_per_step": nbytes_out, "pairs_per_step": pe, "ms_per_step": dt * 1e3,
+                      "matches_device_path": same, "api": "vr180_ctx_run (C ABI host call behind apply_lr/SbsWarper)"}
+        lib.vr180_ctx_destroy(handle)
+        for p in ptrs:
+            lib.vr180_host_free(p)
+        del keep
+    del left, right, out, wp
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_gpu(args) -> dict:
+    import torch
+
+    import vr180_convert_b200 as V
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU path")
+    torch.cuda.set_device(local)
+    V.set_device(local)
+    device = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist_mod.init_process_group("nccl", device_id=device)
+        dist = dist_mod
+    wl = WORKLOADS[args.workload]
+    peak, peak_src = measured_peak()
+    sampler = ClockSampler(local)
+    lib = V._native.lib()
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.vr180_launch_count()
+    main = run_workload(torch, V, args.workload, wl, args.steps, args.warmup, dist, pairs=args.pairs, device=device)
+    clocks = sampler.stop() if rank == 0 else {}
+    # total shards = world * pairs (weak scaling)
+    value = main["value"] * world
+    achieved = main["bytes_per_step"] / (main["ms_per_step"] / 1e3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(args.workload)
+        except Exception:  # noqa: BLE001
+            traffic = None
+    line = {
+        "metric": "SBS equirect output Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 coordinates / u8 fixed-point (INTER_BITS=5) sampling", "data": "synthetic",
+        "config": {"workload": args.workload, "description": wl["desc"], "pairs_per_gpu_per_step": main["pairs"],
+                   "frame_ring": main["ring"], "l2": "inputs+outputs of one step exceed the 126 MB L2 (no flush needed)",
+                   "parallelism": f"frames sharded over {world} GPU(s), no collective"},
+        "gpu_launches": main["launches_per_step"] * args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                     "algorithmic_bytes_per_launch": main["bytes_per_step"],
+                     "source_touched_fraction": main["touched_fraction"], "kernel": "k_remap (1 launch per step)"},
+        "e2e": main.get("e2e"),
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        step, t_maps, threads = cpu_reference_setup(wl, 2 if wl["n"] >= 4096 else 4)
+        sp = 2 if wl["n"] >= 4096 else 4
+        step()
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            step()
+        dt = (time.perf_counter() - t0) / reps
+        n = wl["n"]
+        line["cpu_baseline"] = {
+            "value": sp * n * 2 * n / 1e6 / dt, "unit": "Mpix/s", "cores": os.cpu_count(), "kind": "port",
+            "cv2_threads": threads,
+            "sample": f"{sp} pairs x {reps} reps of cv2.remap x2 + np.concatenate with cached maps (oracle port of "
+                      f"remapper.py:388-398,518); the NumPy get_map restatement took {t_maps:.2f} s for "
+                      f"{2 if wl['tuple_'] else 1} map(s) (single thread) and is reported separately",
+            "map_build_s": t_maps,
+            "value_incl_map_build_for_step_batch":
+                main["pairs"] * n * 2 * n / 1e6 / (t_maps + main["pairs"] * dt / sp)}
+    if args.all_workloads and world == 1:
+        others = {}
+        for name, w in WORKLOADS.items():
+            if name == args.workload:
+                continue
+            r = run_workload(torch, V, name, w, max(3, args.steps // 2), 3, None, want_e2e=False, device=device)
+            a = r["bytes_per_step"] / (r["ms_per_step"] / 1e3) / 1e9
+            others[name] = {"value": r["value"], "unit": "Mpix/s", "ms_per_step": r["ms_per_step"],
+                            "pairs_per_step": r["pairs"], "roofline_frac": a / peak, "achieved_gbs": a}
+        line["other_workloads"] = others
+    line["gpu_launches_total_in_process"] = lib.vr180_launch_count() - launches0
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line if rank == 0 else {}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="8k_rot_poly_linear", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=None, help="stereo pairs per GPU per step")
+    ap.add_argument("--all-workloads", action="store_true", help="also time the other BASELINE configs (N=1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        line = run_reference(args, args.workload, WORKLOADS[args.workload])
+        if line:
+            print(json.dumps(line), flush=True)
+        return
+
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:  # not under torchrun: spawn one rank per GPU ourselves
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), str(Path(__file__).resolve()), *sys.argv[1:]]
+        raise SystemExit(subprocess.call(cmd))
+
+    line = run_gpu(args)
+    if line:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

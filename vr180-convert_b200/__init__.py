@@ -27,7 +27,8 @@ from .transformer import (
     equidistant_to_3d,
     get_radius,
 )
-from .video import SbsWarper, shard_range
+from .shard import gather_shards, max_over_ranks, shard_range
+from .video import SbsWarper
 
 __all__ = [
     "TransformerBase", "ZoomTransformer", "MultiTransformer", "NormalizeTransformer", "PolarRollTransformer",
@@ -35,5 +36,5 @@ __all__ = [
     "Euclidean3DRotator", "Euclidean3DTransformer", "InverseTransformer", "PolynomialScaler", "RectilinearDecoder",
     "apply", "apply_lr", "get_map", "get_radius", "get_radius_smart", "lr_frame", "remap_maps", "set_device",
     "equidistant_to_3d", "equidistant_from_3d", "quaternion", "from_rotation_vector", "from_euler_angles",
-    "rotate_vectors", "SbsWarper", "shard_range",
+    "rotate_vectors", "SbsWarper", "shard_range", "max_over_ranks", "gather_shards",
 ]

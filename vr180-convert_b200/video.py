@@ -21,16 +21,8 @@ import numpy as np
 from . import _native as N
 from .remapper import (BORDER_CONSTANT, INTER_LINEAR, INTER_NEAREST, _border_bytes, _check_modes, host_maps,
                        lower_full)
+from .shard import shard_range  # noqa: F401  (re-exported)
 from .transformer import TransformerBase
-
-
-def shard_range(n_items: int, world_size: int, rank: int) -> range:
-    """Contiguous block partition of `n_items` frames over `world_size` GPUs: rank r owns
-    [r*ceil(n/ws), min(n, (r+1)*ceil(n/ws)))."""
-    if world_size < 1 or not 0 <= rank < world_size:
-        raise ValueError("bad world_size / rank")
-    per = -(-n_items // world_size)
-    return range(min(n_items, rank * per), min(n_items, (rank + 1) * per))
 
 
 class SbsWarper:
