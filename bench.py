@@ -408,7 +408,8 @@ def run_gpu(args) -> dict:
     if rank == 0:
         sampler.start()
     launches0 = lib.vr180_launch_count()
-    main = run_workload(torch, V, args.workload, wl, args.steps, args.warmup, dist, pairs=args.pairs, device=device)
+    main = run_workload(torch, V, args.workload, wl, args.steps, args.warmup, dist, pairs=args.pairs, device=device,
+                        want_e2e=not args.no_e2e)
     clocks = sampler.stop() if rank == 0 else {}
     # total shards = world * pairs (weak scaling)
     value = main["value"] * world
@@ -481,6 +482,7 @@ def main() -> None:
     ap.add_argument("--pairs", type=int, default=None, help="stereo pairs per GPU per step")
     ap.add_argument("--all-workloads", action="store_true", help="also time the other BASELINE configs (N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
