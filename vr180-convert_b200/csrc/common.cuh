@@ -51,12 +51,40 @@ struct DeviceGuard {
     }
 };
 
+// kernel-side description of one vr180_remap call (kernels.cu fills it, kernels.cu / tiled.cu consume it)
+struct ViewArgs {
+    const uint8_t* src;
+    int rows, cols;
+    long long pitch, frame_stride;
+    int map_kind;
+    int chain_idx;  // which of the two kernel-parameter chains
+    const float* xmap;
+    const float* ymap;
+    const int2* fixed;
+    long long map_pitch;
+    const double* radius_dev;
+    int dst_x_offset;
+};
+
+struct RemapArgs {
+    ViewArgs view[2];
+    int n_views, n_frames, share_map;
+    int W, H;
+    int border_mode;
+    uint8_t bv[4];
+    uint8_t* dst;
+    long long dst_pitch, dst_frame_stride;
+    int frames_per_cta;
+};
+
 // internal launchers (kernels.cu); the device is already selected by the caller
 int launch_build_map(const vr180_chain_t* chain, int out_w, int out_h, float* xmap, float* ymap, int64_t pitch,
                      cudaStream_t st);
 int launch_pack_lut(const float* xmap, const float* ymap, int64_t map_pitch, int out_w, int out_h, int32_t* fixed,
                     int64_t fixed_pitch, cudaStream_t st);
 int launch_remap(const vr180_remap_params_t* p, cudaStream_t st);
+int launch_remap_tiled(const RemapArgs& a, int channels, int interp, const vr180_chain_t& c0, const vr180_chain_t& c1,
+                       cudaStream_t st);  // tiled.cu; VR180_ERR_UNSUPPORTED = not eligible, use the generic kernel
 int launch_get_radius(const vr180_image_t* views, int n_views, int n_frames, double threshold, int32_t* transitions,
                       double* radius, cudaStream_t st);
 int validate_chain(const vr180_chain_t* c);

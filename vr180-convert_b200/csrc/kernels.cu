@@ -6,6 +6,7 @@
 //                 straight into the SBS frame, a batch of frames per launch
 //                                                                (cv.remap remapper.py:388-398 + concatenate :518)
 //   k_get_radius  black-pixel transition scan                    (get_radius, transformer.py:108-140)
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -98,31 +99,6 @@ int launch_pack_lut(const float* xmap, const float* ymap, int64_t map_pitch, int
 // ---------------------------------------------------------------------------------------------------------
 // k_remap
 // ---------------------------------------------------------------------------------------------------------
-struct ViewArgs {
-    const uint8_t* src;
-    int rows, cols;
-    long long pitch, frame_stride;
-    int map_kind;
-    int chain_idx;  // which of the two kernel-parameter chains
-    const float* xmap;
-    const float* ymap;
-    const int2* fixed;
-    long long map_pitch;
-    const double* radius_dev;
-    int dst_x_offset;
-};
-
-struct RemapArgs {
-    ViewArgs view[2];
-    int n_views, n_frames, share_map;
-    int W, H;
-    int border_mode;
-    uint8_t bv[4];
-    uint8_t* dst;
-    long long dst_pitch, dst_frame_stride;
-    int frames_per_cta;
-};
-
 template <int C, int INTERP>
 __device__ __forceinline__ void sample_and_store(const Src& s, int sx, int sy, float mx, float my, int border_mode,
                                                  const uint8_t* bv, uint8_t* __restrict__ out) {
@@ -292,6 +268,13 @@ int launch_remap(const vr180_remap_params_t* p, cudaStream_t st) {
     if (interp == VR180_INTER_CUBIC || interp == VR180_INTER_LANCZOS4) {
         const int rc = ensure_tables(st);
         if (rc != VR180_OK) return rc;
+    }
+
+    // fast path: tiled, smem-staged kernel (tiled.cu); VR180_DISABLE_TILED=1 forces the generic gather (A/B tests)
+    static const bool tiled_off = [] { const char* e = getenv("VR180_DISABLE_TILED"); return e && *e == '1'; }();
+    if (!tiled_off) {
+        const int rc = launch_remap_tiled(a, C, interp, *chains[0], *chains[1], st);
+        if (rc != VR180_ERR_UNSUPPORTED) return rc;
     }
 
     // frames per CTA: amortise the coordinate evaluation over up to 16 frames, but keep >= ~4 waves of CTAs
