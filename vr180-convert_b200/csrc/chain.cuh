@@ -27,6 +27,7 @@ namespace vr180 {
 
 constexpr double kHalfPi = 1.5707963267948966;    // np.pi / 2
 constexpr double kSqrt2 = 1.4142135623730951;     // np.sqrt(2)
+constexpr double kTwoOverPi = 0.63661977236758134;  // 1 / (np.pi / 2)
 
 struct ChainState {
     int mode;  // 0 XY, 1 POLAR, 2 VEC3
@@ -43,10 +44,10 @@ __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(
 // VEC3 -> POLAR: equidistant_from_3d (transformer.py:526-529): theta = arccos(vz), phi = atan2(vx, vy),
 // (x, y) = theta * (sin phi, cos phi) == theta * (vx, vy) / hypot(vx, vy).
 __device__ __forceinline__ void vec3_to_polar(ChainState& s) {
-    const double h = sqrt(add_rn(mul_rn(s.vx, s.vx), mul_rn(s.vy, s.vy)));
+    const double h2 = add_rn(mul_rn(s.vx, s.vx), mul_rn(s.vy, s.vy));
     s.r = acos(s.vz);  // NaN when rounding pushed |vz| above 1, as np.arccos does
-    if (h > 0.0) {
-        const double inv = 1.0 / h;
+    if (h2 > 0.0) {
+        const double inv = rsqrt(h2);  // 1 / hypot(vx, vy): one MUFU + Newton steps instead of sqrt + division
         s.ux = s.vx * inv;
         s.uy = s.vy * inv;
     } else {  // atan2(0, 0) = 0 -> (sin, cos) = (0, 1)
@@ -130,10 +131,52 @@ __device__ __forceinline__ double fisheye_theta_to_r(int mapping, double t) {  /
     switch (mapping) {
         case VR180_MAP_RECTILINEAR: return tan(t);
         case VR180_MAP_STEREOGRAPHIC: return mul_rn(2.0, tan(mul_rn(t, 0.5)));
-        case VR180_MAP_EQUIDISTANT: return __ddiv_rn(t, kHalfPi);
+        case VR180_MAP_EQUIDISTANT: return mul_rn(t, kTwoOverPi);  // theta / (pi/2) to 1 ulp, without the division
         case VR180_MAP_EQUISOLID: return mul_rn(kSqrt2, sin(mul_rn(t, 0.5)));
         default: return sin(t);
     }
+}
+
+// ---- one function per op, shared by the interpreter below and the straight-line evaluator of tiled.cu -------
+__device__ __forceinline__ void op_normalize(const double* p, ChainState& s) {  // (x - cx) / scale * 2
+    to_xy(s);
+    s.x = mul_rn(__ddiv_rn(add_rn(s.x, -p[0]), p[2]), 2.0);
+    s.y = mul_rn(__ddiv_rn(add_rn(s.y, -p[1]), p[2]), 2.0);
+}
+__device__ __forceinline__ void op_denormalize(const double* p, ChainState& s) {  // x * sx + cx
+    to_xy(s);
+    s.x = add_rn(mul_rn(s.x, p[0]), p[2]);
+    s.y = add_rn(mul_rn(s.y, p[1]), p[3]);
+}
+__device__ __forceinline__ void op_equirect_enc(int lat_is_y, ChainState& s) {  // transformer.py:545-566
+    to_xy(s);
+    const double lat = mul_rn(lat_is_y ? s.y : s.x, kHalfPi);
+    const double lon = mul_rn(lat_is_y ? s.x : s.y, kHalfPi);
+    double sl, cl, sn, cn;
+    sincos(lat, &sl, &cl);
+    sincos(lon, &sn, &cn);
+    if (lat_is_y) { s.vx = mul_rn(cl, sn); s.vy = sl; }
+    else          { s.vx = sl; s.vy = mul_rn(cl, sn); }
+    s.vz = mul_rn(cl, cn);
+    s.mode = MODE_VEC3;
+}
+__device__ __forceinline__ void op_rot3(const double* R, ChainState& s) {  // v' = R v (quaternion.rotate_vectors)
+    to_vec3(s);
+    const double a = s.vx, b = s.vy, c3 = s.vz;
+    s.vx = add_rn(add_rn(mul_rn(R[0], a), mul_rn(R[1], b)), mul_rn(R[2], c3));
+    s.vy = add_rn(add_rn(mul_rn(R[3], a), mul_rn(R[4], b)), mul_rn(R[5], c3));
+    s.vz = add_rn(add_rn(mul_rn(R[6], a), mul_rn(R[7], b)), mul_rn(R[8], c3));
+}
+// np.polyval(np.flip(coefs_reverse), theta): y = y*x + c, highest power first
+__device__ __forceinline__ void op_poly(const double* coefs, int n, ChainState& s) {
+    to_polar_nonneg(s);
+    double acc = 0.0;
+    for (int i = n - 1; i >= 0; --i) acc = add_rn(mul_rn(acc, s.r), coefs[i]);
+    s.r = acc;
+}
+__device__ __forceinline__ void op_fisheye_dec(int mapping, ChainState& s) {
+    to_polar_nonneg(s);
+    s.r = fisheye_theta_to_r(mapping, s.r);
 }
 
 // Apply ops [first, last) of the chain to the state.  Control flow is uniform across the grid (the op list is
@@ -142,18 +185,8 @@ __device__ __forceinline__ void run_ops(const vr180_chain_t& c, int first, int l
     for (int k = first; k < last; ++k) {
         const vr180_op_t& op = c.ops[k];
         switch (op.code) {
-            case VR180_OP_NORMALIZE: {  // (x - cx) / scale * 2
-                to_xy(s);
-                s.x = mul_rn(__ddiv_rn(add_rn(s.x, -op.p[0]), op.p[2]), 2.0);
-                s.y = mul_rn(__ddiv_rn(add_rn(s.y, -op.p[1]), op.p[2]), 2.0);
-                break;
-            }
-            case VR180_OP_DENORMALIZE: {  // x * sx + cx
-                to_xy(s);
-                s.x = add_rn(mul_rn(s.x, op.p[0]), op.p[2]);
-                s.y = add_rn(mul_rn(s.y, op.p[1]), op.p[3]);
-                break;
-            }
+            case VR180_OP_NORMALIZE: op_normalize(op.p, s); break;
+            case VR180_OP_DENORMALIZE: op_denormalize(op.p, s); break;
             case VR180_OP_DENORMALIZE_INV: {  // (x - cx) / sx
                 to_xy(s);
                 s.x = __ddiv_rn(add_rn(s.x, -op.p[2]), op.p[0]);
@@ -172,19 +205,7 @@ __device__ __forceinline__ void run_ops(const vr180_chain_t& c, int first, int l
                 else { s.x = mul_rn(s.x, op.p[0]); s.y = mul_rn(s.y, op.p[0]); }
                 break;
             }
-            case VR180_OP_EQUIRECT_ENC: {  // transformer.py:545-566
-                to_xy(s);
-                const double lat = mul_rn(op.iparam ? s.y : s.x, kHalfPi);
-                const double lon = mul_rn(op.iparam ? s.x : s.y, kHalfPi);
-                double sl, cl, sn, cn;
-                sincos(lat, &sl, &cl);
-                sincos(lon, &sn, &cn);
-                if (op.iparam) { s.vx = mul_rn(cl, sn); s.vy = sl; }
-                else           { s.vx = sl; s.vy = mul_rn(cl, sn); }
-                s.vz = mul_rn(cl, cn);
-                s.mode = MODE_VEC3;
-                break;
-            }
+            case VR180_OP_EQUIRECT_ENC: op_equirect_enc(op.iparam, s); break;
             case VR180_OP_EQUIRECT_DEC: {  // transformer.py:573-583
                 to_vec3(s);
                 double lat, lon;
@@ -194,24 +215,11 @@ __device__ __forceinline__ void run_ops(const vr180_chain_t& c, int first, int l
                 break;
             }
             case VR180_OP_FISHEYE_ENC: to_polar_nonneg(s); s.r = fisheye_r_to_theta(op.iparam, s.r); break;
-            case VR180_OP_FISHEYE_DEC: to_polar_nonneg(s); s.r = fisheye_theta_to_r(op.iparam, s.r); break;
+            case VR180_OP_FISHEYE_DEC: op_fisheye_dec(op.iparam, s); break;
             case VR180_OP_RECTILINEAR_DEC: to_polar_nonneg(s); s.r = mul_rn(tan(s.r), op.p[0]); break;
             case VR180_OP_RECTILINEAR_DEC_INV: to_polar_nonneg(s); s.r = atan(__ddiv_rn(s.r, op.p[0])); break;
-            case VR180_OP_POLY: {  // np.polyval(np.flip(coefs_reverse), theta): y = y*x + c, highest power first
-                to_polar_nonneg(s);
-                double acc = 0.0;
-                for (int i = op.iparam - 1; i >= 0; --i) acc = add_rn(mul_rn(acc, s.r), op.p[i]);
-                s.r = acc;
-                break;
-            }
-            case VR180_OP_ROT3: {  // v' = R v  (quaternion.rotate_vectors -> 3x3 matrix product)
-                to_vec3(s);
-                const double a = s.vx, b = s.vy, c3 = s.vz;
-                s.vx = add_rn(add_rn(mul_rn(op.p[0], a), mul_rn(op.p[1], b)), mul_rn(op.p[2], c3));
-                s.vy = add_rn(add_rn(mul_rn(op.p[3], a), mul_rn(op.p[4], b)), mul_rn(op.p[5], c3));
-                s.vz = add_rn(add_rn(mul_rn(op.p[6], a), mul_rn(op.p[7], b)), mul_rn(op.p[8], c3));
-                break;
-            }
+            case VR180_OP_POLY: op_poly(op.p, op.iparam, s); break;
+            case VR180_OP_ROT3: op_rot3(op.p, s); break;
             default: break;
         }
     }

@@ -8,17 +8,23 @@
 // frame chunk:
 //   prologue   coordinates of the tile's 1024 pixels, once: analytic chain in float64 (row / column sincos of the
 //              Normalize + EquirectangularEncoder prefix are separable and computed 64x per tile instead of
-//              2048x), or float32 maps, or the fixed-point LUT; quantised exactly like cv::remap (sampler.cuh);
-//              per pixel only {smem offset of tap00, byte shift, packed bilinear weights} stay in registers.
+//              2048x; the standard chain shape runs as straight-line code, anything else through the op
+//              interpreter of chain.cuh), or float32 maps, or the fixed-point LUT; quantised exactly like
+//              cv::remap (sampler.cuh); per pixel only {smem offset of tap00, byte shift, packed bilinear
+//              weights} stay in registers.
 //   bbox       block-wide min / max of the integer source coordinates -> the tile's source rectangle.
-//   pipeline   for every (frame, eye): the source rectangle is staged into shared memory by the TMA unit, one
-//              1-D bulk copy per source row (cp.async.bulk ... mbarrier::complete_tx), 3 stages deep, so the copy
-//              of item k+2 overlaps the sampling of item k.
-//   sampling   6 LDS.32 per pixel (2 rows x 12 bytes), funnel shifts to byte-align, PRMT to gather the 4 taps of
-//              each channel into one register, 2 x dp4a per channel against the packed weights:
-//                  out = (sum_t w_t p_t + 512) >> 10,  w_t = 32 * wh_t + wl_t   (identical to sample_linear)
-//   store      the warp's 32 pixels x 3 bytes are re-packed with two shuffles into 24 aligned words and written
-//              as one 96-byte row segment straight into the eye's half of the SBS frame.
+//   pipeline   for every (frame, eye): the source rectangle is staged into shared memory with 16-byte cp.async
+//              (LDGSTS, L1 bypass), 3 stages deep, so the copy of item k+2 overlaps the sampling of item k.
+//              (A variant with one TMA bulk copy per source row measured 27 % slower: the per-row UBLKCP issue
+//              loop costs 8 issue slots per ~130-byte row -- profiles/bench_r1_v2_tiled_bulkcopy.json.)
+//   sampling   a warp samples an 8 x 4 pixel patch: 6 LDS.32 per pixel (2 rows x 12 bytes), funnel shifts to
+//              byte-align, PRMT to gather the 4 taps of each channel into one register, 2 x dp2a (16-bit weight x
+//              8-bit pixel) per channel:
+//                  (sum_t w_t p_t + 512) >> 10  ==  (sum_t 64 w_t p_t + 32768) >> 16
+//              so the result is byte 2 of the dp2a chain and is packed with two PRMTs.
+//   store      each patch row's 8 pixels x 3 bytes are re-packed with two shuffles into 6 aligned words and
+//              written straight into the eye's half of the SBS frame (the 4 patches of a tile row complete the
+//              96-byte segment, so L2 merges them into full sectors).
 // Tiles whose footprint leaves the source image, is unbounded (NaN / huge coordinates) or exceeds the staging
 // buffer, and partial edge tiles, take the per-pixel global-memory gather of sampler.cuh inside the same kernel.
 #include <cstdlib>
@@ -31,76 +37,37 @@ namespace vr180 {
 namespace tiled {
 
 constexpr int kTile = 32;       // output tile edge
-constexpr int kPx = 4;          // rows per thread: row = warp + 8 * k
+constexpr int kPx = 4;          // pixels per thread.  A warp covers an 8 x 4 pixel patch per k (lane & 7 = column,
+                                // lane >> 3 = row): its source footprint is a compact 2-D patch whatever the local
+                                // direction of the map, which keeps the tap loads (nearly) free of bank conflicts;
+                                // warp w owns patch column w & 3 and patch rows (w >> 2) + 2 * k
 constexpr int kThreads = 256;
 constexpr int kStages = 3;
-constexpr int kPitchS = 208;    // bytes between staged source rows (52 words: rows shift by 20 banks)
-constexpr int kMaxRows = 68;
-constexpr int kStageBytes = 14208;  // kPitchS * kMaxRows + 64 B slack for the aligned 12-byte tap windows
-constexpr int kSmemBytes = kStages * kStageBytes + 4 * 32 * 8 + 64 + 8 * 4 * 4;
+constexpr int kPitchS = 224;    // bytes between staged source rows: 56 words = -8 banks per row, so the <= 8-word
+                                // row segments of a patch's 4 source rows fall into disjoint banks
+constexpr int kMaxRows = 64;
+constexpr int kStageBytes = kPitchS * kMaxRows;
+constexpr int kTailBytes = 128;  // slack for the aligned 12-byte tap windows of the last staged row
+constexpr int kSmemBytes = kStages * kStageBytes + kTailBytes + 4 * 32 * 8 + 8 * 4 * 4;
+
+// The standard chain shape, lowered once on the host (see match_std_chain):
+//   Normalize, EquirectangularEncoder, [Euclidean3DRotator], [PolynomialScaler], FisheyeDecoder("equidistant"),
+//   Denormalize
+struct StdChain {
+    int valid, lat_is_y, has_rot, n_poly;
+    double norm[3];   // cx, cy, scale
+    double R[9];
+    double poly[VR180_MAX_OP_PARAMS];
+    double den[4];    // sx, sy, cx, cy
+};
+
+struct TiledParams {
+    int tiles_x;
+    int sep_prefix;  // generic chains only: ops[0..1] = Normalize, EquirectangularEncoder
+    StdChain std[2];
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-// 1-D bulk copy global -> shared through the TMA unit; completion is signalled on `bar` in bytes.
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
-// Packed bilinear weights of one pixel: byte t of WL / WH holds wl_t / wh_t for taps t = (00, 01, 10, 11).
-__device__ __forceinline__ void pack_weights(int ax, int ay, uint32_t& WL, uint32_t& WH) {
-    const int w00 = (32 - ax) * (32 - ay), w01 = ax * (32 - ay), w10 = (32 - ax) * ay, w11 = ax * ay;
-    WL = (w00 & 31) | ((w01 & 31) << 8) | ((w10 & 31) << 16) | ((w11 & 31) << 24);
-    WH = (w00 >> 5) | ((w01 >> 5) << 8) | ((w10 >> 5) << 16) | ((w11 >> 5) << 24);
-}
-
-// One output pixel from the staged tile: returns the three result bytes packed [c0 c1 c2 0].
-__device__ __forceinline__ uint32_t sample3(const uint32_t* __restrict__ r0, int sh, uint32_t WL, uint32_t WH) {
-    const uint32_t* r1 = r0 + kPitchS / 4;
-    const uint32_t a0 = r0[0], a1 = r0[1], a2 = r0[2];
-    const uint32_t b0 = r1[0], b1 = r1[1], b2 = r1[2];
-    // byte-align: lo = [c0 c1 c2 c0'], hi = [c1' c2' . .]  (primed = the pixel at ix + 1)
-    const uint32_t r0lo = __funnelshift_r(a0, a1, sh), r0hi = __funnelshift_r(a1, a2, sh);
-    const uint32_t r1lo = __funnelshift_r(b0, b1, sh), r1hi = __funnelshift_r(b1, b2, sh);
-    const uint32_t q0 = __byte_perm(r0lo, r1lo, 0x7430);  // channel 0 taps [p00 p01 p10 p11]
-    const uint32_t t0 = __byte_perm(r0lo, r0hi, 0x5241);  // row 0: [c1 c1' c2 c2']
-    const uint32_t t1 = __byte_perm(r1lo, r1hi, 0x5241);
-    const uint32_t q1 = __byte_perm(t0, t1, 0x5410);
-    const uint32_t q2 = __byte_perm(t0, t1, 0x7632);
-    const uint32_t s0 = __dp4a(q0, WH, 0u) * 32u + __dp4a(q0, WL, 512u);
-    const uint32_t s1 = __dp4a(q1, WH, 0u) * 32u + __dp4a(q1, WL, 512u);
-    const uint32_t s2 = __dp4a(q2, WH, 0u) * 32u + __dp4a(q2, WL, 512u);
-    return (s0 >> 10) | ((s1 >> 10) << 8) | ((s2 >> 10) << 16);
-}
-
-struct PixelConst {  // per output pixel, constant over the frames of the batch
-    int boff[kPx];      // byte offset (4-aligned) of the 12-byte tap window of row 0 inside a stage buffer
-    int sh[kPx];        // 8 * (tap00 byte offset & 3)
-    uint32_t WL[kPx], WH[kPx];
-};
-struct TileGeom {
-    int nrows, wbytes;
-    long long src_off, dst_off;
-};
 
 // 16-byte asynchronous copy global -> shared (LDGSTS, L1 bypass); completion through commit / wait groups.
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -112,25 +79,60 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Packed bilinear weights of one pixel as 16-bit lanes: W01 = {64 w00, 64 w01}, W23 = {64 w10, 64 w11}.
+// w00 = 1024 (ax = ay = 0, all other weights 0) is encoded as 65535: (65535 p + 32768) >> 16 is still exactly p.
+__device__ __forceinline__ void pack_weights(int ax, int ay, uint32_t& W01, uint32_t& W23) {
+    const int w00 = (32 - ax) * (32 - ay), w01 = ax * (32 - ay), w10 = (32 - ax) * ay, w11 = ax * ay;
+    W01 = (uint32_t)min(64 * w00, 65535) | ((uint32_t)(64 * w01) << 16);
+    W23 = (uint32_t)(64 * w10) | ((uint32_t)(64 * w11) << 16);
+}
+
+// One output pixel from the staged tile (r0 = aligned window of tap row 0): the three result bytes [c0 c1 c2 0].
+__device__ __forceinline__ uint32_t sample3(const uint32_t* __restrict__ r0, int sh, uint32_t W01, uint32_t W23) {
+    const uint32_t* r1 = r0 + kPitchS / 4;
+    const uint32_t a0 = r0[0], a1 = r0[1], a2 = r0[2];
+    const uint32_t b0 = r1[0], b1 = r1[1], b2 = r1[2];
+    // byte-align: lo = [c0 c1 c2 c0'], hi = [c1' c2' . .]  (primed = the pixel at ix + 1)
+    const uint32_t r0lo = __funnelshift_r(a0, a1, sh), r0hi = __funnelshift_r(a1, a2, sh);
+    const uint32_t r1lo = __funnelshift_r(b0, b1, sh), r1hi = __funnelshift_r(b1, b2, sh);
+    const uint32_t q0 = __byte_perm(r0lo, r1lo, 0x7430);  // channel 0 taps [p00 p01 p10 p11]
+    const uint32_t t0 = __byte_perm(r0lo, r0hi, 0x5241);  // row 0: [c1 c1' c2 c2']
+    const uint32_t t1 = __byte_perm(r1lo, r1hi, 0x5241);
+    const uint32_t q1 = __byte_perm(t0, t1, 0x5410);
+    const uint32_t q2 = __byte_perm(t0, t1, 0x7632);
+    // (sum_t w_t p_t + 512) >> 10 == (sum_t 64 w_t p_t + 32768) >> 16: the result is byte 2 of s (s < 2^24)
+    const uint32_t s0 = __dp2a_hi(W23, q0, __dp2a_lo(W01, q0, 32768u));
+    const uint32_t s1 = __dp2a_hi(W23, q1, __dp2a_lo(W01, q1, 32768u));
+    const uint32_t s2 = __dp2a_hi(W23, q2, __dp2a_lo(W01, q2, 32768u));
+    return __byte_perm(__byte_perm(s0, s1, 0x0062), s2, 0x7610);
+}
+
+struct PixelConst {  // per output pixel, constant over the frames of the batch
+    int boff[kPx];      // byte offset (4-aligned) of the 12-byte tap window of row 0 inside a stage buffer
+    int sh[kPx];        // 8 * (tap00 byte offset & 3)
+    uint32_t W01[kPx], W23[kPx];
+};
+struct TileGeom {
+    int nrows, wbytes;
+    long long src_off, dst_off;
+};
+
 // The frame loop of one tile.  Items are (frame, view) pairs in frame-major order; item n lives in stage n % 3.
-// NV = views sampled with this CTA's coordinates (2 when both eyes share the map).
-// BULK = true : one cp.async.bulk (TMA unit, UBLKCP) per source row, issued by threads 0..nrows-1, mbarrier tx-count
-//        false: 16-byte cp.async (LDGSTS) chunks, thread t copies chunk (t & 15) of rows t >> 4, +16, +32, ...
-template <int NV, bool BULK>
+// NV = views sampled with this CTA's coordinates (2 when both eyes share the map).  The loop is unrolled over
+// lcm(NV, 3) items so that the stage and the view of every item are compile-time constants.
+template <int NV>
 __device__ __forceinline__ void frame_loop(const RemapArgs& a, int v_begin, int f0, int f1, const PixelConst& pc,
-                                           const TileGeom& tg, uint8_t* smem, uint64_t* s_bar) {
+                                           const TileGeom& tg, uint8_t* smem) {
     const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t bar0 = smem_u32(s_bar);
-    const uint32_t tx_bytes = (uint32_t)(tg.wbytes * tg.nrows);
-    // loader role of this thread
-    const int lrow = BULK ? tid : (tid >> 4), lcol = BULK ? 0 : (tid & 15) * 16;
-    const bool loader = BULK ? (tid < tg.nrows) : (lcol < tg.wbytes);
-    const uint32_t stage0 = smem_u32(smem) + lrow * kPitchS + lcol;  // this thread's slot in stage 0
-    // word `lane` (< 24) of a 96-byte output row segment = bytes of pixels p0 and p0 + 1
-    const int p0 = (4 * lane) / 3, sub = 4 * lane - 3 * p0;
+    // loader role: thread t copies 16-byte chunk (t & 15) (< 14) of rows (t >> 4), +16, +32, +48
+    const int lrow = tid >> 4, lcol = (tid & 15) * 16;
+    const bool loader = lcol < tg.wbytes;
+    const uint32_t lslot = smem_u32(smem) + lrow * kPitchS + lcol;
+    // word j = lane & 7 (< 6) of the 24-byte row segment of this lane's patch row = bytes of pixels p0 and p0 + 1
+    const int wj = lane & 7, p0 = (4 * wj) / 3, sub = 4 * wj - 3 * p0;
     const uint32_t out_sel = sub == 0 ? 0x4210u : (sub == 1 ? 0x5421u : 0x6542u);
-    const int p0c = min(p0, 31), p1c = min(p0 + 1, 31);
-    const bool writer = lane < 24;
+    const int p0c = (lane & 24) + min(p0, 7), p1c = (lane & 24) + min(p0 + 1, 7);
+    const bool writer = wj < 6;
     const long long pitch8 = 8 * a.dst_pitch;
 
     const uint8_t* nsrc[NV];  // source position (this thread's loader slot) of the next item of view v to issue
@@ -145,110 +147,88 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, int v_begin, int 
         dst[v] = a.dst + (long long)f0 * a.dst_frame_stride + tg.dst_off + (long long)vw.dst_x_offset * 3;
     }
     const int n_items = (f1 - f0) * NV;
+    const int passes = (tg.nrows - lrow + 15) >> 4;  // rows lrow, lrow + 16, ... < nrows
 
     auto issue = [&](int v, int st) {  // stage the next item of view v into stage st
-        if (BULK) {
-            if (loader) bulk_g2s(stage0 + st * kStageBytes, nsrc[v], (uint32_t)tg.wbytes, bar0 + st * 8);
-        } else {
-            if (loader) {
-                const uint8_t* s = nsrc[v];
-                uint32_t d = stage0 + st * kStageBytes;
-                for (int r = lrow; r < tg.nrows; r += 16, s += src_pitch16[v], d += 16 * kPitchS) cp_async16(d, s);
+        if (loader) {
+            const uint8_t* s = nsrc[v];
+            const uint32_t d = lslot + st * kStageBytes;
+#pragma unroll
+            for (int m = 0; m < kMaxRows / 16; ++m) {
+                if (m < passes) cp_async16(d + m * 16 * kPitchS, s);
+                s += src_pitch16[v];
             }
-            cp_async_commit();
         }
+        cp_async_commit();
         nsrc[v] += src_fs[v];
     };
 
     // prime the pipeline: items 0 and 1
-    if (BULK) {
-        if (tid == 0) {
-            mbar_arrive_expect_tx(bar0, tx_bytes);
-            if (n_items > 1) mbar_arrive_expect_tx(bar0 + 8, tx_bytes);
-        }
-        __syncthreads();
-    }
     issue(0, 0);
     if (NV == 2) issue(1, 1);
     else if (n_items > 1) issue(0, 1);
-    else if (!BULK) cp_async_commit();  // keep the group count uniform
+    else cp_async_commit();  // keep the group count uniform
 
-    int st = 0, st2 = 2;       // stage of the current item / of item + 2
-    uint32_t parity = 0;       // phase parity of stage `st`
-    int remaining = n_items;   // items not yet sampled, including the current one
-    for (int f = f0; f < f1; ++f) {
+    constexpr int U = (NV == 2) ? 6 : 3;
+    for (int base = 0; base < n_items; base += U) {
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            const bool more = remaining > 2;
-            if (BULK) {
-                if (more && tid == 0) mbar_arrive_expect_tx(bar0 + st2 * 8, tx_bytes);
-                __syncthreads();  // every thread is done reading stage st2 (it held item - 1)
-                if (more) issue(v, st2);
-                mbar_wait(bar0 + st * 8, parity);
-            } else {
+        for (int u = 0; u < U; ++u) {
+            if (base + u < n_items) {
+                const int st = u % kStages, st2 = (u + 2) % kStages, v = u % NV;
                 cp_async_wait<1>();  // this thread's chunks of the current item have landed
-                __syncthreads();     // ... everybody's have, and everybody is done reading stage st2
-                if (more) issue(v, st2);
+                __syncthreads();     // ... everybody's have, and everybody is done reading stage st2 (item - 1)
+                if (base + u + 2 < n_items) issue(v, st2);
                 else cp_async_commit();
-            }
 
-            const uint8_t* buf = smem + st * kStageBytes;
-            uint32_t res[kPx];
+                const uint8_t* buf = smem + st * kStageBytes;
+                uint32_t res[kPx];
 #pragma unroll
-            for (int k = 0; k < kPx; ++k)
-                res[k] = sample3(reinterpret_cast<const uint32_t*>(buf + pc.boff[k]), pc.sh[k], pc.WL[k], pc.WH[k]);
+                for (int k = 0; k < kPx; ++k)
+                    res[k] = sample3(reinterpret_cast<const uint32_t*>(buf + pc.boff[k]), pc.sh[k], pc.W01[k], pc.W23[k]);
 #pragma unroll
-            for (int k = 0; k < kPx; ++k) {
-                const uint32_t pa = __shfl_sync(0xffffffffu, res[k], p0c);
-                const uint32_t pb = __shfl_sync(0xffffffffu, res[k], p1c);
-                if (writer) *reinterpret_cast<uint32_t*>(dst[v] + k * pitch8) = __byte_perm(pa, pb, out_sel);
+                for (int k = 0; k < kPx; ++k) {
+                    const uint32_t pa = __shfl_sync(0xffffffffu, res[k], p0c);
+                    const uint32_t pb = __shfl_sync(0xffffffffu, res[k], p1c);
+                    if (writer) *reinterpret_cast<uint32_t*>(dst[v] + k * pitch8) = __byte_perm(pa, pb, out_sel);
+                }
+                dst[v] += a.dst_frame_stride;
             }
-            dst[v] += a.dst_frame_stride;
-            --remaining;
-            if (++st == kStages) { st = 0; parity ^= 1u; }
-            if (++st2 == kStages) st2 = 0;
         }
     }
 }
 
-template <bool BULK>
 __global__ void __launch_bounds__(kThreads, 4)
 k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_chain_t chain0,
-             const __grid_constant__ vr180_chain_t chain1, int tiles_x, int sep_prefix) {
+             const __grid_constant__ vr180_chain_t chain1, const __grid_constant__ TiledParams tp) {
     extern __shared__ __align__(128) uint8_t smem[];
-    double* s_trig = reinterpret_cast<double*>(smem + kStages * kStageBytes);          // [4][32]
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + 1024);  // [kStages]
-    int* s_red = reinterpret_cast<int*>(smem + kStages * kStageBytes + 1024 + 64);       // [8][4]
+    double* s_trig = reinterpret_cast<double*>(smem + kStages * kStageBytes + kTailBytes);  // [4][32]
+    int* s_red = reinterpret_cast<int*>(smem + kStages * kStageBytes + kTailBytes + 1024);  // [8][4]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int tx = blockIdx.x % tp.tiles_x, ty = blockIdx.x / tp.tiles_x;
     const int x0 = tx * kTile, y0 = ty * kTile;
     const int g = blockIdx.y;  // map group: the view whose coordinates drive this CTA
     const ViewArgs& mv = a.view[g];
     const int v_begin = g, v_end = a.share_map ? a.n_views : g + 1, nv = v_end - v_begin;
     const int f0 = blockIdx.z * a.frames_per_cta, f1 = min(a.n_frames, f0 + a.frames_per_cta);
-    const int i = x0 + lane;
+    const int lx = 8 * (warp & 3) + (lane & 7), ly = 4 * (warp >> 2) + (lane >> 3);  // pixel k: (lx, ly + 8 k)
+    const int i = x0 + lx;
     const bool full_tile = (x0 + kTile <= a.W) && (y0 + kTile <= a.H);
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(smem_u32(&s_bar[s]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
 
     // ---- coordinates of this thread's 4 pixels ------------------------------------------------------------
     int sx[kPx], sy[kPx];
     if (mv.map_kind == VR180_MAPSRC_ANALYTIC) {
         const vr180_chain_t& ch = mv.chain_idx ? chain1 : chain0;
-        if (sep_prefix) {
+        const StdChain& sc = tp.std[mv.chain_idx ? 1 : 0];
+        if (sc.valid || tp.sep_prefix) {
             // Normalize + EquirectangularEncoder prefix (transformer.py:153-164, :545-566): the angle of a column
             // (row) depends on the column (row) only, so its sincos is evaluated once per tile column (row).
             if (tid < 64) {
                 const bool is_row = tid >= 32;
                 const int idx = tid & 31;
-                const vr180_op_t& nm = ch.ops[0];
+                const double* nm = ch.ops[0].p;
                 const double c = (double)((is_row ? y0 : x0) + idx);
-                const double n = mul_rn(__ddiv_rn(add_rn(c, -(is_row ? nm.p[1] : nm.p[0])), nm.p[2]), 2.0);
+                const double n = mul_rn(__ddiv_rn(add_rn(c, -(is_row ? nm[1] : nm[0])), nm[2]), 2.0);
                 double sv, cv;
                 sincos(mul_rn(n, kHalfPi), &sv, &cv);
                 s_trig[(is_row ? 64 : 0) + idx] = sv;
@@ -256,12 +236,10 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
             }
             __syncthreads();
             const bool lat_is_y = ch.ops[1].iparam != 0;
-            const double s_col = s_trig[lane], c_col = s_trig[32 + lane];
-#pragma unroll 1
-            for (int k = 0; k < kPx; ++k) {
-                const int r = warp + 8 * k;
+            const double s_col = s_trig[lx], c_col = s_trig[32 + lx];
+            auto seed = [&](int k, ChainState& s) {
+                const int r = ly + 8 * k;
                 const double s_row = s_trig[64 + r], c_row = s_trig[96 + r];
-                ChainState s;
                 s.mode = MODE_VEC3;
                 s.x = s.y = s.r = s.ux = s.uy = 0.0;
                 if (lat_is_y) {  // lat from the row, lon from the column
@@ -273,24 +251,47 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                     s.vy = mul_rn(c_col, s_row);
                     s.vz = mul_rn(c_col, c_row);
                 }
-                run_ops(ch, 2, ch.n_ops, s);
-                to_xy(s);
-                sx[k] = quantise(__double2float_rn(s.x));  // astype(float32) then cvRound(x * 32)
-                sy[k] = quantise(__double2float_rn(s.y));
+            };
+            if (sc.valid) {  // straight-line: the same op functions, in the same order, as the interpreter would run
+#pragma unroll
+                for (int k = 0; k < kPx; ++k) {
+                    ChainState s;
+                    seed(k, s);
+                    if (sc.has_rot) op_rot3(sc.R, s);
+                    if (sc.n_poly >= 0) op_poly(sc.poly, sc.n_poly, s);
+                    op_fisheye_dec(VR180_MAP_EQUIDISTANT, s);
+                    op_denormalize(sc.den, s);
+                    sx[k] = quantise(__double2float_rn(s.x));  // astype(float32) then cvRound(x * 32)
+                    sy[k] = quantise(__double2float_rn(s.y));
+                }
+            } else {
+#pragma unroll 1
+                for (int k = 0; k < kPx; ++k) {
+                    ChainState s;
+                    seed(k, s);
+                    run_ops(ch, 2, ch.n_ops, s);
+                    to_xy(s);
+                    const int qx = quantise(__double2float_rn(s.x)), qy = quantise(__double2float_rn(s.y));
+#pragma unroll
+                    for (int kk = 0; kk < kPx; ++kk)
+                        if (kk == k) { sx[kk] = qx; sy[kk] = qy; }
+                }
             }
         } else {
 #pragma unroll 1
             for (int k = 0; k < kPx; ++k) {
                 double xs, ys;
-                eval_chain(ch, i, y0 + warp + 8 * k, xs, ys);
-                sx[k] = quantise(__double2float_rn(xs));
-                sy[k] = quantise(__double2float_rn(ys));
+                eval_chain(ch, i, y0 + ly + 8 * k, xs, ys);
+                const int qx = quantise(__double2float_rn(xs)), qy = quantise(__double2float_rn(ys));
+#pragma unroll
+                for (int kk = 0; kk < kPx; ++kk)
+                    if (kk == k) { sx[kk] = qx; sy[kk] = qy; }
             }
         }
     } else {
 #pragma unroll
         for (int k = 0; k < kPx; ++k) {
-            const int j = y0 + warp + 8 * k;
+            const int j = y0 + ly + 8 * k;
             sx[k] = sy[k] = (int)0x80000000;
             if (i < a.W && j < a.H) {
                 if (mv.map_kind == VR180_MAPSRC_FLOAT2) {
@@ -325,7 +326,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         s_red[warp * 4 + 2] = mny;
         s_red[warp * 4 + 3] = mxy;
     }
-    __syncthreads();  // also publishes the mbarrier initialisation
+    __syncthreads();
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w) {
         mnx = min(mnx, s_red[w * 4 + 0]);
@@ -341,21 +342,22 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
 
     if (!fast) {  // per-pixel gather from global memory with full border handling (rare tiles)
         if (i < a.W) {
-#pragma unroll 1
+#pragma unroll
             for (int k = 0; k < kPx; ++k) {
-                const int j = y0 + warp + 8 * k;
-                if (j >= a.H) break;
-                for (int f = f0; f < f1; ++f) {
-                    uint8_t* drow = a.dst + (long long)f * a.dst_frame_stride + (long long)j * a.dst_pitch;
-                    for (int v = v_begin; v < v_end; ++v) {
-                        const ViewArgs& vw = a.view[v];
-                        Src s{vw.src + (long long)f * vw.frame_stride, vw.rows, vw.cols, vw.pitch};
-                        int px[3];
-                        sample_linear<3>(s, sx[k], sy[k], VR180_BORDER_CONSTANT, a.bv, px);
-                        uint8_t* o = drow + (long long)(vw.dst_x_offset + i) * 3;
-                        o[0] = (uint8_t)px[0];
-                        o[1] = (uint8_t)px[1];
-                        o[2] = (uint8_t)px[2];
+                const int j = y0 + ly + 8 * k;
+                if (j < a.H) {
+                    for (int f = f0; f < f1; ++f) {
+                        uint8_t* drow = a.dst + (long long)f * a.dst_frame_stride + (long long)j * a.dst_pitch;
+                        for (int v = v_begin; v < v_end; ++v) {
+                            const ViewArgs& vw = a.view[v];
+                            Src s{vw.src + (long long)f * vw.frame_stride, vw.rows, vw.cols, vw.pitch};
+                            int px[3];
+                            sample_linear<3>(s, sx[k], sy[k], VR180_BORDER_CONSTANT, a.bv, px);
+                            uint8_t* o = drow + (long long)(vw.dst_x_offset + i) * 3;
+                            o[0] = (uint8_t)px[0];
+                            o[1] = (uint8_t)px[1];
+                            o[2] = (uint8_t)px[2];
+                        }
                     }
                 }
             }
@@ -371,18 +373,43 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         const int off = (iy - mny) * kPitchS + 3 * ix - bx0;
         pc.boff[k] = off & ~3;
         pc.sh[k] = (off & 3) * 8;
-        pack_weights(sx[k] & 31, sy[k] & 31, pc.WL[k], pc.WH[k]);
+        pack_weights(sx[k] & 31, sy[k] & 31, pc.W01[k], pc.W23[k]);
     }
     TileGeom tg;
     tg.nrows = nrows;
     tg.wbytes = wbytes;
     tg.src_off = (long long)mny * v0.pitch + bx0;  // first byte of the source rectangle inside a frame
-    tg.dst_off = (long long)(y0 + warp) * a.dst_pitch + (long long)x0 * 3 + lane * 4;
-    if (nv == 2) frame_loop<2, BULK>(a, v_begin, f0, f1, pc, tg, smem, s_bar);
-    else frame_loop<1, BULK>(a, v_begin, f0, f1, pc, tg, smem, s_bar);
+    tg.dst_off = (long long)(y0 + ly) * a.dst_pitch + (long long)(x0 + 8 * (warp & 3)) * 3 + (lane & 7) * 4;
+    if (nv == 2) frame_loop<2>(a, v_begin, f0, f1, pc, tg, smem);
+    else frame_loop<1>(a, v_begin, f0, f1, pc, tg, smem);
 }
 
 }  // namespace tiled
+
+// Host: recognise the standard chain shape (see StdChain).
+static void match_std_chain(const vr180_chain_t& c, tiled::StdChain& out) {
+    memset(&out, 0, sizeof(out));
+    out.n_poly = -1;
+    if (c.n_ops < 4 || c.ops[0].code != VR180_OP_NORMALIZE || c.ops[1].code != VR180_OP_EQUIRECT_ENC) return;
+    memcpy(out.norm, c.ops[0].p, sizeof(out.norm));
+    out.lat_is_y = c.ops[1].iparam != 0;
+    int k = 2;
+    if (c.ops[k].code == VR180_OP_ROT3) {
+        out.has_rot = 1;
+        memcpy(out.R, c.ops[k].p, sizeof(out.R));
+        ++k;
+    }
+    if (k < c.n_ops && c.ops[k].code == VR180_OP_POLY) {
+        out.n_poly = c.ops[k].iparam;
+        memcpy(out.poly, c.ops[k].p, sizeof(out.poly));
+        ++k;
+    }
+    if (k + 2 != c.n_ops || c.ops[k].code != VR180_OP_FISHEYE_DEC || c.ops[k].iparam != VR180_MAP_EQUIDISTANT ||
+        c.ops[k + 1].code != VR180_OP_DENORMALIZE)
+        return;
+    memcpy(out.den, c.ops[k + 1].p, sizeof(out.den));
+    out.valid = 1;
+}
 
 // Host-side eligibility + launch.  Returns VR180_ERR_UNSUPPORTED when the request is outside the fast path (the
 // caller then launches the generic k_remap); any other value is final.
@@ -395,7 +422,7 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
     for (int v = 0; v < a0.n_views; ++v) {
         const ViewArgs& vw = a0.view[v];
         if (((uintptr_t)vw.src & 15) || (vw.pitch & 15) || (vw.frame_stride & 15) || vw.pitch < (long long)vw.cols * 3)
-            return VR180_ERR_UNSUPPORTED;  // bulk copies need 16-byte aligned rows
+            return VR180_ERR_UNSUPPORTED;  // 16-byte cp.async needs 16-byte aligned rows
         if (vw.rows != a0.view[0].rows || vw.cols != a0.view[0].cols) return VR180_ERR_UNSUPPORTED;
         if ((vw.dst_x_offset * 3) & 3) return VR180_ERR_UNSUPPORTED;
     }
@@ -403,19 +430,19 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
         if (a0.view[g].map_kind == VR180_MAPSRC_ANALYTIC && a0.view[g].radius_dev) return VR180_ERR_UNSUPPORTED;
     if (((uintptr_t)a0.dst & 3) || (a0.dst_pitch & 3) || (a0.dst_frame_stride & 3)) return VR180_ERR_UNSUPPORTED;
 
-    // staging engine: 16-byte cp.async chunks (default) or one TMA bulk copy per source row (VR180_TILED_STAGE=bulk)
-    static const bool bulk = [] { const char* e = getenv("VR180_TILED_STAGE"); return e && !strcmp(e, "bulk"); }();
     static std::atomic<int> attr_done[64];
     int dev = 0;
     VR180_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !attr_done[dev].load(std::memory_order_acquire)) {
-        VR180_CUDA(cudaFuncSetAttribute(k_warp_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        VR180_CUDA(cudaFuncSetAttribute(k_warp_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        VR180_CUDA(cudaFuncSetAttribute(k_warp_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_done[dev].store(1, std::memory_order_release);
     }
 
     RemapArgs a = a0;
+    TiledParams tp;
+    memset(&tp, 0, sizeof(tp));
     const int tiles_x = (a.W + kTile - 1) / kTile, tiles_y = (a.H + kTile - 1) / kTile;
+    tp.tiles_x = tiles_x;
     const long long tiles = (long long)tiles_x * tiles_y * n_groups;
     // frames per CTA: the coordinates are evaluated once per CTA, so keep the chunk as large as the grid allows
     int fpc = a.n_frames;
@@ -426,12 +453,15 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
     auto is_sep = [](const vr180_chain_t& c) {
         return c.n_ops >= 2 && c.ops[0].code == VR180_OP_NORMALIZE && c.ops[1].code == VR180_OP_EQUIRECT_ENC;
     };
-    int sep = 1;
-    for (int g = 0; g < n_groups; ++g)
-        if (a.view[g].map_kind == VR180_MAPSRC_ANALYTIC && !is_sep(a.view[g].chain_idx ? c1 : c0)) sep = 0;
+    tp.sep_prefix = 1;
+    for (int g = 0; g < n_groups; ++g) {
+        if (a.view[g].map_kind != VR180_MAPSRC_ANALYTIC) continue;
+        const vr180_chain_t& c = a.view[g].chain_idx ? c1 : c0;
+        if (!is_sep(c)) tp.sep_prefix = 0;
+        match_std_chain(c, tp.std[a.view[g].chain_idx ? 1 : 0]);
+    }
     dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)n_groups, (unsigned)chunks);
-    if (bulk) k_warp_tiled<true><<<grid, kThreads, kSmemBytes, st>>>(a, c0, c1, tiles_x, sep);
-    else k_warp_tiled<false><<<grid, kThreads, kSmemBytes, st>>>(a, c0, c1, tiles_x, sep);
+    k_warp_tiled<<<grid, kThreads, kSmemBytes, st>>>(a, c0, c1, tp);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     VR180_CUDA(cudaGetLastError());
     return VR180_OK;
