@@ -13,21 +13,25 @@
 //              cv::remap (sampler.cuh); per pixel only {smem offset of tap00, byte shift, packed bilinear
 //              weights} stay in registers.
 //   bbox       block-wide min / max of the integer source coordinates -> the tile's source rectangle.
-//   pipeline   for every (frame, eye): the source rectangle is staged into shared memory with 16-byte cp.async
-//              (LDGSTS, L1 bypass), 3 stages deep, so the copy of item k+2 overlaps the sampling of item k.
-//              (A variant with one TMA bulk copy per source row measured 27 % slower: the per-row UBLKCP issue
-//              loop costs 8 issue slots per ~130-byte row -- profiles/bench_r1_v2_tiled_bulkcopy.json.)
+//   pipeline   for every (frame, eye) item the source rectangle is fetched by TMA (cp.async.bulk.tensor.3d over the
+//              (bytes, rows, frames) view of the source batch, boxes of 8 rows, completion on an mbarrier), 3
+//              stages deep: the loads of items k+1 .. k+3 are in flight while item k is sampled.  TMA's
+//              out-of-bounds zero fill IS BORDER_CONSTANT(0), so tiles that straddle the source edge stay on the
+//              fast path.  No LSU instruction touches the source (the previous cp.async version spent 23 % of its
+//              shared-memory wavefronts on LDGSTS, profiles/r1_v4_*).
 //   sampling   a warp samples an 8 x 4 pixel patch: 6 LDS.32 per pixel (2 rows x 12 bytes), funnel shifts to
-//              byte-align, PRMT to gather the 4 taps of each channel into one register, 2 x dp2a (16-bit weight x
-//              8-bit pixel) per channel:
+//              byte-align, PRMT to pair the taps, 2 x dp2a (16-bit weight x 8-bit pixel) per channel:
 //                  (sum_t w_t p_t + 512) >> 10  ==  (sum_t 64 w_t p_t + 32768) >> 16
 //              so the result is byte 2 of the dp2a chain and is packed with two PRMTs.
-//   store      each patch row's 8 pixels x 3 bytes are re-packed with two shuffles into 6 aligned words and
-//              written straight into the eye's half of the SBS frame (the 4 patches of a tile row complete the
-//              96-byte segment, so L2 merges them into full sectors).
-// Tiles whose footprint leaves the source image, is unbounded (NaN / huge coordinates) or exceeds the staging
-// buffer, and partial edge tiles, take the per-pixel global-memory gather of sampler.cuh inside the same kernel.
+//   store      each patch row's 8 pixels x 3 bytes are re-packed with two shuffles into 6 words of a dense 32 x 96
+//              byte output tile in shared memory; one elected thread writes the tile into the eye's half of the
+//              SBS frame with a TMA store (full 32-byte sectors, no STG).
+// Tiles whose footprint is unbounded (NaN / huge coordinates) or exceeds the staging buffer, and partial edge
+// tiles, take the per-pixel global-memory gather of sampler.cuh inside the same kernel.
+#include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint
+
 #include <cstdlib>
+#include <mutex>
 
 #include "chain.cuh"
 #include "common.cuh"
@@ -43,12 +47,19 @@ constexpr int kPx = 4;          // pixels per thread.  A warp covers an 8 x 4 pi
                                 // warp w owns patch column w & 3 and patch rows (w >> 2) + 2 * k
 constexpr int kThreads = 256;
 constexpr int kStages = 3;
-constexpr int kPitchS = 224;    // bytes between staged source rows: 56 words = -8 banks per row, so the <= 8-word
-                                // row segments of a patch's 4 source rows fall into disjoint banks
+constexpr int kBoxRows = 8;     // rows per TMA box
+constexpr int kPitchNarrow = 160, kPitchWide = 224;  // staged row pitch = TMA box width (bytes).  40 / 56 words =
+                                // +8 / -8 banks per row, so the <= 8-word row segments of a patch's 4 source rows
+                                // fall into disjoint banks
 constexpr int kMaxRows = 64;
-constexpr int kStageBytes = kPitchS * kMaxRows;
-constexpr int kTailBytes = 128;  // slack for the aligned 12-byte tap windows of the last staged row
-constexpr int kSmemBytes = kStages * kStageBytes + kTailBytes + 4 * 32 * 8 + 8 * 4 * 4;
+constexpr int kStageBytes = kPitchWide * kMaxRows;  // 14336 = 112 * 128
+constexpr int kOutTileBytes = kTile * kTile * 3;    // dense 32 x 96 B output tile = one TMA store box
+constexpr int kOutBufs = 3;
+constexpr int kOffOut = kStages * kStageBytes;
+constexpr int kOffTrig = kOffOut + kOutBufs * kOutTileBytes;
+constexpr int kOffRed = kOffTrig + 4 * 32 * 8;
+constexpr int kOffBar = kOffRed + 8 * 4 * 4;
+constexpr int kSmemBytes = kOffBar + kStages * 8 + 128;  // + slack for the aligned 12-byte tap window of the last row
 
 // The standard chain shape, lowered once on the host (see match_std_chain):
 //   Normalize, EquirectangularEncoder, [Euclidean3DRotator], [PolynomialScaler], FisheyeDecoder("equidistant"),
@@ -67,16 +78,49 @@ struct TiledParams {
     StdChain std[2];
 };
 
+// TMA descriptors of one launch (kernel parameter; the TMA unit reads them from the parameter bank).
+struct alignas(64) TmaMaps {
+    CUtensorMap src[2][2];  // [view][0: 160-byte boxes, 1: 224-byte boxes], uint8 (cols * 3, rows, frames), box (w, 8, 1)
+    CUtensorMap dst;        // uint8 (dst_pitch, H, frames), box (96, 32, 1)
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// 16-byte asynchronous copy global -> shared (LDGSTS, L1 bypass); completion through commit / wait groups.
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+// ---- mbarrier / TMA primitives (PTX ISA 8.x, sm_90+) -----------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// global (tensor map, coordinates {x bytes, row, frame}) -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+            "r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
+        : "memory");
+}
+// shared -> global (tensor map, coordinates), tracked by the thread's bulk async-group
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int x, int y, int z, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(x),
+                 "r"(y), "r"(z), "r"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+__device__ __forceinline__ void bulk_wait_read() {  // all but the N newest bulk groups have finished READING smem
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
 // Packed bilinear weights of one pixel as 16-bit lanes: W01 = {64 w00, 64 w01}, W23 = {64 w10, 64 w11}.
@@ -88,22 +132,21 @@ __device__ __forceinline__ void pack_weights(int ax, int ay, uint32_t& W01, uint
 }
 
 // One output pixel from the staged tile (r0 = aligned window of tap row 0): the three result bytes [c0 c1 c2 0].
+template <int PITCH>
 __device__ __forceinline__ uint32_t sample3(const uint32_t* __restrict__ r0, int sh, uint32_t W01, uint32_t W23) {
-    const uint32_t* r1 = r0 + kPitchS / 4;
+    const uint32_t* r1 = r0 + PITCH / 4;
     const uint32_t a0 = r0[0], a1 = r0[1], a2 = r0[2];
     const uint32_t b0 = r1[0], b1 = r1[1], b2 = r1[2];
     // byte-align: lo = [c0 c1 c2 c0'], hi = [c1' c2' . .]  (primed = the pixel at ix + 1)
     const uint32_t r0lo = __funnelshift_r(a0, a1, sh), r0hi = __funnelshift_r(a1, a2, sh);
     const uint32_t r1lo = __funnelshift_r(b0, b1, sh), r1hi = __funnelshift_r(b1, b2, sh);
-    const uint32_t q0 = __byte_perm(r0lo, r1lo, 0x7430);  // channel 0 taps [p00 p01 p10 p11]
-    const uint32_t t0 = __byte_perm(r0lo, r0hi, 0x5241);  // row 0: [c1 c1' c2 c2']
-    const uint32_t t1 = __byte_perm(r1lo, r1hi, 0x5241);
-    const uint32_t q1 = __byte_perm(t0, t1, 0x5410);
-    const uint32_t q2 = __byte_perm(t0, t1, 0x7632);
+    const uint32_t q0 = __byte_perm(r0lo, r1lo, 0x7430);  // channel 0: [p00 p01 | p10 p11]
+    const uint32_t t0 = __byte_perm(r0lo, r0hi, 0x5241);  // row 0: [c1 c1' | c2 c2']
+    const uint32_t t1 = __byte_perm(r1lo, r1hi, 0x5241);  // row 1
     // (sum_t w_t p_t + 512) >> 10 == (sum_t 64 w_t p_t + 32768) >> 16: the result is byte 2 of s (s < 2^24)
     const uint32_t s0 = __dp2a_hi(W23, q0, __dp2a_lo(W01, q0, 32768u));
-    const uint32_t s1 = __dp2a_hi(W23, q1, __dp2a_lo(W01, q1, 32768u));
-    const uint32_t s2 = __dp2a_hi(W23, q2, __dp2a_lo(W01, q2, 32768u));
+    const uint32_t s1 = __dp2a_lo(W23, t1, __dp2a_lo(W01, t0, 32768u));
+    const uint32_t s2 = __dp2a_hi(W23, t1, __dp2a_hi(W01, t0, 32768u));
     return __byte_perm(__byte_perm(s0, s1, 0x0062), s2, 0x7610);
 }
 
@@ -113,98 +156,111 @@ struct PixelConst {  // per output pixel, constant over the frames of the batch
     uint32_t W01[kPx], W23[kPx];
 };
 struct TileGeom {
-    int nrows, wbytes;
-    long long src_off, dst_off;
+    int nrows;          // source rows of the tile's rectangle
+    int bx0, mny;       // first source byte column (16-aligned, may be negative) and first source row
+    int x0, y0;         // output tile origin
 };
 
-// The frame loop of one tile.  Items are (frame, view) pairs in frame-major order; item n lives in stage n % 3.
-// NV = views sampled with this CTA's coordinates (2 when both eyes share the map).  The loop is unrolled over
-// lcm(NV, 3) items so that the stage and the view of every item are compile-time constants.
-template <int NV>
-__device__ __forceinline__ void frame_loop(const RemapArgs& a, int v_begin, int f0, int f1, const PixelConst& pc,
-                                           const TileGeom& tg, uint8_t* smem) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    // loader role: thread t copies 16-byte chunk (t & 15) (< 14) of rows (t >> 4), +16, +32, +48
-    const int lrow = tid >> 4, lcol = (tid & 15) * 16;
-    const bool loader = lcol < tg.wbytes;
-    const uint32_t lslot = smem_u32(smem) + lrow * kPitchS + lcol;
+// The frame loop of one tile.  Items are (frame, view) pairs in frame-major order; item n lives in stage n % 3 and
+// its output tile in out buffer n % 3.  NV = views sampled with this CTA's coordinates (2 when both eyes share the
+// map).  The loop is unrolled over lcm(NV, 3) items so that stage, view and mbarrier parity of every item are
+// compile-time constants.
+//
+// Synchronisation per item n (one __syncthreads):
+//   wait full[n % 3]          the TMA boxes of item n have landed
+//   sample, STS out[n % 3]    out[n % 3] was last read by the TMA store of item n - 3 (finished, see below)
+//   fence.proxy.async         generic-proxy writes -> visible to the async proxy (TMA store)
+//   thread 0: bulk wait_group.read 1   the store of item n - 2 has finished reading out[(n + 1) % 3]
+//   __syncthreads             everybody has written out[n % 3] and is done reading stage n % 3
+//   thread 0: TMA store of out[n % 3]; TMA loads of item n + 3 into stage n % 3
+template <int NV, int PITCH>
+__device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm, int v_begin, int f0, int f1,
+                                           const PixelConst& pc, const TileGeom& tg, uint8_t* smem) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // word j = lane & 7 (< 6) of the 24-byte row segment of this lane's patch row = bytes of pixels p0 and p0 + 1
     const int wj = lane & 7, p0 = (4 * wj) / 3, sub = 4 * wj - 3 * p0;
     const uint32_t out_sel = sub == 0 ? 0x4210u : (sub == 1 ? 0x5421u : 0x6542u);
     const int p0c = (lane & 24) + min(p0, 7), p1c = (lane & 24) + min(p0 + 1, 7);
     const bool writer = wj < 6;
-    const long long pitch8 = 8 * a.dst_pitch;
+    // this lane's word inside a dense 32 x 96 B output tile: row 4 (warp >> 2) + (lane >> 3) + 8 k
+    const int ooff = (4 * (warp >> 2) + (lane >> 3)) * 96 + (warp & 3) * 24 + wj * 4;
+    const uint32_t s_stage = smem_u32(smem), s_out = s_stage + kOffOut, s_bar = s_stage + kOffBar;
+    uint8_t* const outp = smem + kOffOut + ooff;
 
-    const uint8_t* nsrc[NV];  // source position (this thread's loader slot) of the next item of view v to issue
-    uint8_t* dst[NV];
-    long long src_fs[NV], src_pitch16[NV];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-        const ViewArgs& vw = a.view[v_begin + v];
-        nsrc[v] = vw.src + (long long)f0 * vw.frame_stride + tg.src_off + (long long)lrow * vw.pitch + lcol;
-        src_fs[v] = vw.frame_stride;
-        src_pitch16[v] = 16 * vw.pitch;
-        dst[v] = a.dst + (long long)f0 * a.dst_frame_stride + tg.dst_off + (long long)vw.dst_x_offset * 3;
-    }
     const int n_items = (f1 - f0) * NV;
-    const int passes = (tg.nrows - lrow + 15) >> 4;  // rows lrow, lrow + 16, ... < nrows
-
-    auto issue = [&](int v, int st) {  // stage the next item of view v into stage st
-        if (loader) {
-            const uint8_t* s = nsrc[v];
-            const uint32_t d = lslot + st * kStageBytes;
+    const int nbox = (tg.nrows + kBoxRows - 1) / kBoxRows;
+    const uint32_t tx_bytes = (uint32_t)(nbox * kBoxRows * PITCH);
+    int dst_x[NV];
 #pragma unroll
-            for (int m = 0; m < kMaxRows / 16; ++m) {
-                if (m < passes) cp_async16(d + m * 16 * kPitchS, s);
-                s += src_pitch16[v];
-            }
-        }
-        cp_async_commit();
-        nsrc[v] += src_fs[v];
+    for (int v = 0; v < NV; ++v) dst_x[v] = (a.view[v_begin + v].dst_x_offset + tg.x0) * 3;
+
+    auto issue = [&](int v, int f, int st) {  // thread 0: fetch the source rectangle of (frame f, view v) into stage st
+        const uint32_t bar = s_bar + st * 8;
+        const CUtensorMap* map = &tm.src[v_begin + v][PITCH == kPitchWide ? 1 : 0];
+        mbar_expect_tx(bar, tx_bytes);
+        for (int b = 0; b < nbox; ++b)
+            tma_load_3d(s_stage + st * kStageBytes + b * kBoxRows * PITCH, map, tg.bx0, tg.mny + b * kBoxRows, f, bar);
     };
 
-    // prime the pipeline: items 0 and 1
-    issue(0, 0);
-    if (NV == 2) issue(1, 1);
-    else if (n_items > 1) issue(0, 1);
-    else cp_async_commit();  // keep the group count uniform
+    if (tid == 0) {
+#pragma unroll
+        for (int n = 0; n < kStages; ++n)
+            if (n < n_items) issue(n % NV, f0 + n / NV, n);
+    }
 
     constexpr int U = (NV == 2) ? 6 : 3;
+    uint32_t it_parity = 0;  // U == 3: every stage is used once per outer iteration
     for (int base = 0; base < n_items; base += U) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (base + u < n_items) {
-                const int st = u % kStages, st2 = (u + 2) % kStages, v = u % NV;
-                cp_async_wait<1>();  // this thread's chunks of the current item have landed
-                __syncthreads();     // ... everybody's have, and everybody is done reading stage st2 (item - 1)
-                if (base + u + 2 < n_items) issue(v, st2);
-                else cp_async_commit();
+                const int st = u % kStages, v = u % NV;
+                const int f = f0 + (base + u) / NV;
+                const uint32_t parity = (U == 6) ? (uint32_t)(u / kStages) : it_parity;
+                mbar_wait(s_bar + st * 8, parity);
 
                 const uint8_t* buf = smem + st * kStageBytes;
                 uint32_t res[kPx];
 #pragma unroll
                 for (int k = 0; k < kPx; ++k)
-                    res[k] = sample3(reinterpret_cast<const uint32_t*>(buf + pc.boff[k]), pc.sh[k], pc.W01[k], pc.W23[k]);
+                    res[k] = sample3<PITCH>(reinterpret_cast<const uint32_t*>(buf + pc.boff[k]), pc.sh[k], pc.W01[k],
+                                            pc.W23[k]);
 #pragma unroll
                 for (int k = 0; k < kPx; ++k) {
                     const uint32_t pa = __shfl_sync(0xffffffffu, res[k], p0c);
                     const uint32_t pb = __shfl_sync(0xffffffffu, res[k], p1c);
-                    if (writer) *reinterpret_cast<uint32_t*>(dst[v] + k * pitch8) = __byte_perm(pa, pb, out_sel);
+                    if (writer)
+                        *reinterpret_cast<uint32_t*>(outp + st * kOutTileBytes + k * 8 * 96) = __byte_perm(pa, pb, out_sel);
                 }
-                dst[v] += a.dst_frame_stride;
+                fence_proxy_async();
+                if (tid == 0) bulk_wait_read<1>();
+                __syncthreads();
+                if (tid == 0) {
+                    tma_store_3d(&tm.dst, dst_x[v], tg.y0, f, s_out + st * kOutTileBytes);
+                    bulk_commit();
+                    if (base + u + kStages < n_items) issue((u + kStages) % NV, f0 + (base + u + kStages) / NV, st);
+                }
             }
         }
+        it_parity ^= 1u;
     }
+    if (tid == 0) bulk_wait_read<0>();  // shared memory must stay valid until the last store has read it
 }
 
 __global__ void __launch_bounds__(kThreads, 4)
 k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_chain_t chain0,
-             const __grid_constant__ vr180_chain_t chain1, const __grid_constant__ TiledParams tp) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    double* s_trig = reinterpret_cast<double*>(smem + kStages * kStageBytes + kTailBytes);  // [4][32]
-    int* s_red = reinterpret_cast<int*>(smem + kStages * kStageBytes + kTailBytes + 1024);  // [8][4]
+             const __grid_constant__ vr180_chain_t chain1, const __grid_constant__ TiledParams tp,
+             const __grid_constant__ TmaMaps tm) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    double* s_trig = reinterpret_cast<double*>(smem + kOffTrig);  // [4][32]
+    int* s_red = reinterpret_cast<int*>(smem + kOffRed);          // [8][4]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < kStages; ++st) mbar_init(smem_u32(smem + kOffBar) + st * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy (TMA)
+    }
     const int tx = blockIdx.x % tp.tiles_x, ty = blockIdx.x / tp.tiles_x;
     const int x0 = tx * kTile, y0 = ty * kTile;
     const int g = blockIdx.y;  // map group: the view whose coordinates drive this CTA
@@ -337,8 +393,11 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     const ViewArgs& v0 = a.view[v_begin];
     const int bx0 = (3 * mnx) & ~15, bx1 = (3 * (mxx + 2) + 15) & ~15;  // byte range of the taps, 16-byte granules
     const int wbytes = bx1 - bx0, nrows = mxy + 2 - mny;
-    const bool fast = full_tile && mnx >= 0 && mny >= 0 && mxx + 1 < v0.cols && mxy + 1 < v0.rows && wbytes <= kPitchS &&
-                      nrows <= kMaxRows && (long long)bx1 <= v0.pitch;
+    // Taps outside the source read TMA's zero fill = BORDER_CONSTANT(0); only unbounded footprints (NaN / huge
+    // coordinates saturate to +-32768) and partial edge tiles leave the fast path.
+    const bool fast = full_tile && wbytes <= kPitchWide && nrows <= kMaxRows && mnx > -32768 && mny > -32768 &&
+                      mxx < 32767 && mxy < 32767;
+    (void)v0;
 
     if (!fast) {  // per-pixel gather from global memory with full border handling (rare tiles)
         if (i < a.W) {
@@ -366,22 +425,29 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     }
 
     // ---- per-pixel constants of the frame loop ------------------------------------------------------------
+    const int pitch = wbytes <= kPitchNarrow ? kPitchNarrow : kPitchWide;
     PixelConst pc;
 #pragma unroll
     for (int k = 0; k < kPx; ++k) {
         const int ix = sx[k] >> kInterBits, iy = sy[k] >> kInterBits;
-        const int off = (iy - mny) * kPitchS + 3 * ix - bx0;
+        const int off = (iy - mny) * pitch + 3 * ix - bx0;
         pc.boff[k] = off & ~3;
         pc.sh[k] = (off & 3) * 8;
         pack_weights(sx[k] & 31, sy[k] & 31, pc.W01[k], pc.W23[k]);
     }
     TileGeom tg;
     tg.nrows = nrows;
-    tg.wbytes = wbytes;
-    tg.src_off = (long long)mny * v0.pitch + bx0;  // first byte of the source rectangle inside a frame
-    tg.dst_off = (long long)(y0 + ly) * a.dst_pitch + (long long)(x0 + 8 * (warp & 3)) * 3 + (lane & 7) * 4;
-    if (nv == 2) frame_loop<2>(a, v_begin, f0, f1, pc, tg, smem);
-    else frame_loop<1>(a, v_begin, f0, f1, pc, tg, smem);
+    tg.bx0 = bx0;
+    tg.mny = mny;
+    tg.x0 = x0;
+    tg.y0 = y0;
+    if (pitch == kPitchNarrow) {
+        if (nv == 2) frame_loop<2, kPitchNarrow>(a, tm, v_begin, f0, f1, pc, tg, smem);
+        else frame_loop<1, kPitchNarrow>(a, tm, v_begin, f0, f1, pc, tg, smem);
+    } else {
+        if (nv == 2) frame_loop<2, kPitchWide>(a, tm, v_begin, f0, f1, pc, tg, smem);
+        else frame_loop<1, kPitchWide>(a, tm, v_begin, f0, f1, pc, tg, smem);
+    }
 }
 
 }  // namespace tiled
@@ -411,6 +477,40 @@ static void match_std_chain(const vr180_chain_t& c, tiled::StdChain& out) {
     out.valid = 1;
 }
 
+// ---- TMA descriptors (host) ---------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// uint8 tensor (row_bytes, rows, frames) with byte strides (pitch, frame_stride); box (box_w, box_h, 1).
+// Out-of-bounds box elements are filled with zeros on loads and dropped on stores.
+static bool encode_u8_3d(CUtensorMap* out, const void* base, long long row_bytes, long long rows, long long frames,
+                         long long pitch, long long frame_stride, int box_w, int box_h) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    if (frames <= 1 || frame_stride < pitch * rows) frame_stride = ((pitch * rows + 15) / 16) * 16;  // unused when frames == 1
+    const cuuint64_t dims[3] = {(cuuint64_t)row_bytes, (cuuint64_t)rows, (cuuint64_t)(frames < 1 ? 1 : frames)};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Host-side eligibility + launch.  Returns VR180_ERR_UNSUPPORTED when the request is outside the fast path (the
 // caller then launches the generic k_remap); any other value is final.
 int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr180_chain_t& c0, const vr180_chain_t& c1,
@@ -421,14 +521,32 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
     const int n_groups = a0.share_map ? 1 : a0.n_views;
     for (int v = 0; v < a0.n_views; ++v) {
         const ViewArgs& vw = a0.view[v];
+        // TMA: 16-byte aligned base and strides
         if (((uintptr_t)vw.src & 15) || (vw.pitch & 15) || (vw.frame_stride & 15) || vw.pitch < (long long)vw.cols * 3)
-            return VR180_ERR_UNSUPPORTED;  // 16-byte cp.async needs 16-byte aligned rows
+            return VR180_ERR_UNSUPPORTED;
+        if (a0.n_frames > 1 && vw.frame_stride < vw.pitch * vw.rows) return VR180_ERR_UNSUPPORTED;
         if (vw.rows != a0.view[0].rows || vw.cols != a0.view[0].cols) return VR180_ERR_UNSUPPORTED;
-        if ((vw.dst_x_offset * 3) & 3) return VR180_ERR_UNSUPPORTED;
     }
     for (int g = 0; g < n_groups; ++g)
         if (a0.view[g].map_kind == VR180_MAPSRC_ANALYTIC && a0.view[g].radius_dev) return VR180_ERR_UNSUPPORTED;
-    if (((uintptr_t)a0.dst & 3) || (a0.dst_pitch & 3) || (a0.dst_frame_stride & 3)) return VR180_ERR_UNSUPPORTED;
+    if (((uintptr_t)a0.dst & 15) || (a0.dst_pitch & 15) || (a0.dst_frame_stride & 15)) return VR180_ERR_UNSUPPORTED;
+    if (a0.n_frames > 1 && a0.dst_frame_stride < a0.dst_pitch * a0.H) return VR180_ERR_UNSUPPORTED;
+
+    TmaMaps tm;
+    memset(&tm, 0, sizeof(tm));
+    for (int v = 0; v < a0.n_views; ++v) {
+        const ViewArgs& vw = a0.view[v];
+        for (int w = 0; w < 2; ++w)
+            if (!encode_u8_3d(&tm.src[v][w], vw.src, (long long)vw.cols * 3, vw.rows, a0.n_frames, vw.pitch, vw.frame_stride,
+                              w ? kPitchWide : kPitchNarrow, kBoxRows))
+                return VR180_ERR_UNSUPPORTED;
+    }
+    if (a0.n_views == 1) {
+        tm.src[1][0] = tm.src[0][0];
+        tm.src[1][1] = tm.src[0][1];
+    }
+    if (!encode_u8_3d(&tm.dst, a0.dst, a0.dst_pitch, a0.H, a0.n_frames, a0.dst_pitch, a0.dst_frame_stride, kTile * 3, kTile))
+        return VR180_ERR_UNSUPPORTED;
 
     static std::atomic<int> attr_done[64];
     int dev = 0;
@@ -461,7 +579,7 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
         match_std_chain(c, tp.std[a.view[g].chain_idx ? 1 : 0]);
     }
     dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)n_groups, (unsigned)chunks);
-    k_warp_tiled<<<grid, kThreads, kSmemBytes, st>>>(a, c0, c1, tp);
+    k_warp_tiled<<<grid, kThreads, kSmemBytes, st>>>(a, c0, c1, tp, tm);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     VR180_CUDA(cudaGetLastError());
     return VR180_OK;
