@@ -44,22 +44,23 @@ constexpr int kTile = 32;       // output tile edge
 constexpr int kPx = 4;          // pixels per thread.  A warp covers an 8 x 4 pixel patch per k (lane & 7 = column,
                                 // lane >> 3 = row): its source footprint is a compact 2-D patch whatever the local
                                 // direction of the map, which keeps the tap loads (nearly) free of bank conflicts;
-                                // warp w owns patch column w & 3 and patch rows (w >> 2) + 2 * k
-constexpr int kThreads = 256;
-constexpr int kStages = 3;
-constexpr int kBoxRows = 8;     // rows per TMA box
+                                // warp w owns output rows 4 w .. 4 w + 3 of the tile, k = patch column (8 px each)
+constexpr int kSamplers = 256;  // 8 sampling warps
+constexpr int kThreads = kSamplers + 32;  // + the TMA producer warp
+constexpr int kMaxStages = 8;   // ring depth is chosen per tile: kStageArea / (bytes of the tile's source rectangle)
+constexpr int kRowsMin = 32, kRowsStep = 8, kRowSizes = 5;  // TMA load box heights: 32, 40, 48, 56, 64 rows
 constexpr int kPitchNarrow = 160, kPitchWide = 224;  // staged row pitch = TMA box width (bytes).  40 / 56 words =
                                 // +8 / -8 banks per row, so the <= 8-word row segments of a patch's 4 source rows
                                 // fall into disjoint banks
 constexpr int kMaxRows = 64;
-constexpr int kStageBytes = kPitchWide * kMaxRows;  // 14336 = 112 * 128
+constexpr int kStageArea = 40960;  // >= 2 stages of the largest admissible rectangle (64 rows x 224 B)
 constexpr int kOutTileBytes = kTile * kTile * 3;    // dense 32 x 96 B output tile = one TMA store box
-constexpr int kOutBufs = 3;
-constexpr int kOffOut = kStages * kStageBytes;
+constexpr int kOutBufs = 4;                         // power of two
+constexpr int kOffOut = kStageArea;
 constexpr int kOffTrig = kOffOut + kOutBufs * kOutTileBytes;
 constexpr int kOffRed = kOffTrig + 4 * 32 * 8;
-constexpr int kOffBar = kOffRed + 8 * 4 * 4;
-constexpr int kSmemBytes = kOffBar + kStages * 8 + 128;  // + slack for the aligned 12-byte tap window of the last row
+constexpr int kOffBar = kOffRed + 8 * 4 * 4;        // full[kMaxStages], empty[kMaxStages], ofull[kOutBufs], oempty[kOutBufs]
+constexpr int kSmemBytes = kOffBar + (2 * kMaxStages + 2 * kOutBufs) * 8;
 
 // The standard chain shape, lowered once on the host (see match_std_chain):
 //   Normalize, EquirectangularEncoder, [Euclidean3DRotator], [PolynomialScaler], FisheyeDecoder("equidistant"),
@@ -80,8 +81,8 @@ struct TiledParams {
 
 // TMA descriptors of one launch (kernel parameter; the TMA unit reads them from the parameter bank).
 struct alignas(64) TmaMaps {
-    CUtensorMap src[2][2];  // [view][0: 160-byte boxes, 1: 224-byte boxes], uint8 (cols * 3, rows, frames), box (w, 8, 1)
-    CUtensorMap dst;        // uint8 (dst_pitch, H, frames), box (96, 32, 1)
+    CUtensorMap src[2][2][kRowSizes];  // [view][0: 160-byte, 1: 224-byte boxes][box rows 32 + 8 r]: uint8 (cols * 3, rows, frames)
+    CUtensorMap dst;                   // uint8 (dst_pitch, H, frames), box (96, 32, 1)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,6 +93,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -135,8 +139,11 @@ __device__ __forceinline__ void pack_weights(int ax, int ay, uint32_t& W01, uint
 template <int PITCH>
 __device__ __forceinline__ uint32_t sample3(const uint32_t* __restrict__ r0, int sh, uint32_t W01, uint32_t W23) {
     const uint32_t* r1 = r0 + PITCH / 4;
-    const uint32_t a0 = r0[0], a1 = r0[1], a2 = r0[2];
-    const uint32_t b0 = r1[0], b1 = r1[1], b2 = r1[2];
+    // the 6 tap bytes start at byte sh / 8 of the window: only an offset of 3 reaches into the third word, so 3/4 of
+    // the lanes skip that load (fewer active lanes = fewer bank conflicts)
+    const bool third = sh == 24;
+    const uint32_t a0 = r0[0], a1 = r0[1], a2 = third ? r0[2] : 0u;
+    const uint32_t b0 = r1[0], b1 = r1[1], b2 = third ? r1[2] : 0u;
     // byte-align: lo = [c0 c1 c2 c0'], hi = [c1' c2' . .]  (primed = the pixel at ix + 1)
     const uint32_t r0lo = __funnelshift_r(a0, a1, sh), r0hi = __funnelshift_r(a1, a2, sh);
     const uint32_t r1lo = __funnelshift_r(b0, b1, sh), r1hi = __funnelshift_r(b1, b2, sh);
@@ -161,90 +168,107 @@ struct TileGeom {
     int x0, y0;         // output tile origin
 };
 
-// The frame loop of one tile.  Items are (frame, view) pairs in frame-major order; item n lives in stage n % 3 and
-// its output tile in out buffer n % 3.  NV = views sampled with this CTA's coordinates (2 when both eyes share the
-// map).  The loop is unrolled over lcm(NV, 3) items so that stage, view and mbarrier parity of every item are
-// compile-time constants.
+// The frame loop of one tile.  Items are (frame, view) pairs in frame-major order.  NV = views sampled with this
+// CTA's coordinates (2 when both eyes share the map).
 //
-// Synchronisation per item n (one __syncthreads):
-//   wait full[n % 3]          the TMA boxes of item n have landed
-//   sample, STS out[n % 3]    out[n % 3] was last read by the TMA store of item n - 3 (finished, see below)
-//   fence.proxy.async         generic-proxy writes -> visible to the async proxy (TMA store)
-//   thread 0: bulk wait_group.read 1   the store of item n - 2 has finished reading out[(n + 1) % 3]
-//   __syncthreads             everybody has written out[n % 3] and is done reading stage n % 3
-//   thread 0: TMA store of out[n % 3]; TMA loads of item n + 3 into stage n % 3
+// Warp-specialised: warps 0-7 sample (4 output rows each), lane 0 of warp 8 drives the TMA unit and nothing else,
+// so no sampling warp ever blocks on a copy.  TMA work is kept to TWO operations per item (one load box = the whole
+// source rectangle, one store box = the whole 32 x 96 B output tile): a version with 5 load boxes + 8 per-warp
+// store boxes per item measured TMA-issue bound (~50 clk per operation, profiles/r1_v7_*).
+//
+// The staging area is a ring of S stages of exactly the tile's footprint (box rows x PITCH bytes), so a typical
+// tile (40 rows x 160 B = 6.4 KB) gets S = 6 and the loads run D = S - 2 items ahead of the sampling.
+// No CTA-wide barrier; four kinds of mbarrier:
+//   full[s]    (1 + tx bytes)  the box of the item in stage s has landed; the sampling warps wait on it
+//   empty[s]   (8)             one arrive per sampling warp when it is done reading stage s; the producer waits
+//                              before re-filling (with D = S - 2 that is the stage of item n - 2)
+//   ofull[o]   (8)             one arrive per sampling warp when its 4 rows of the output tile are in out buffer o
+//                              (4 deep); the producer waits, then issues the TMA store
+//   oempty[o]  (1)             the producer arrives when the store that last used out buffer o has finished reading
+//                              it (bulk wait_group.read); the sampling warps wait before rewriting it (item n - 4)
 template <int NV, int PITCH>
 __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm, int v_begin, int f0, int f1,
                                            const PixelConst& pc, const TileGeom& tg, uint8_t* smem) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t s_stage = smem_u32(smem), s_full = s_stage + kOffBar, s_empty = s_full + kMaxStages * 8;
+    const uint32_t s_ofull = s_empty + kMaxStages * 8, s_oempty = s_ofull + kOutBufs * 8, s_out = s_stage + kOffOut;
+
+    const int n_items = (f1 - f0) * NV;
+    const int rsel = tg.nrows <= kRowsMin ? 0 : (tg.nrows - kRowsMin + kRowsStep - 1) / kRowsStep;
+    const int stage_bytes = (kRowsMin + rsel * kRowsStep) * PITCH;  // multiple of 128
+    const int S = min(kMaxStages, kStageArea / stage_bytes), D = S <= 3 ? S - 1 : S - 2;
+
+    if (warp == kSamplers / 32) {  // ---- producer ----
+        if (lane != 0) return;
+        const CUtensorMap* const map0 = &tm.src[v_begin][PITCH == kPitchWide ? 1 : 0][rsel];
+        const int dst_x0 = (a.view[v_begin].dst_x_offset + tg.x0) * 3;
+        const int dst_x1 = (a.view[v_begin + NV - 1].dst_x_offset + tg.x0) * 3;
+        int p_item = 0, p_stage = 0, p_use = 0;  // next item to fetch, its stage, how often that stage was filled
+        auto load = [&]() {
+            const uint32_t bar = s_full + p_stage * 8;
+            const int v = (NV == 2) ? (p_item & 1) : 0, f = f0 + ((NV == 2) ? (p_item >> 1) : p_item);
+            if (p_use > 0) mbar_wait(s_empty + p_stage * 8, (uint32_t)(p_use + 1) & 1u);
+            mbar_expect_tx(bar, (uint32_t)stage_bytes);
+            tma_load_3d(s_stage + p_stage * stage_bytes, map0 + v * (2 * kRowSizes), tg.bx0, tg.mny, f, bar);
+            ++p_item;
+            if (++p_stage == S) { p_stage = 0; ++p_use; }
+        };
+        for (int n = 0; n < D && n < n_items; ++n) load();
+        for (int n = 0; n < n_items; ++n) {
+            if (n + D < n_items) load();
+            const int o = n & (kOutBufs - 1);
+            const int v = (NV == 2) ? (n & 1) : 0, f = f0 + ((NV == 2) ? (n >> 1) : n);
+            mbar_wait(s_ofull + o * 8, (uint32_t)(n / kOutBufs) & 1u);  // every sampling warp has written item n
+            tma_store_3d(&tm.dst, v ? dst_x1 : dst_x0, tg.y0, f, s_out + o * kOutTileBytes);
+            bulk_commit();
+            if (n >= 1) {
+                bulk_wait_read<1>();  // the store of item n - 1 has finished reading its out buffer
+                mbar_arrive(s_oempty + ((n - 1) & (kOutBufs - 1)) * 8);
+            }
+        }
+        bulk_wait_read<0>();  // shared memory must stay valid until the last store has read it
+        return;
+    }
+
+    // ---- sampling warps ----
     // word j = lane & 7 (< 6) of the 24-byte row segment of this lane's patch row = bytes of pixels p0 and p0 + 1
     const int wj = lane & 7, p0 = (4 * wj) / 3, sub = 4 * wj - 3 * p0;
     const uint32_t out_sel = sub == 0 ? 0x4210u : (sub == 1 ? 0x5421u : 0x6542u);
     const int p0c = (lane & 24) + min(p0, 7), p1c = (lane & 24) + min(p0 + 1, 7);
     const bool writer = wj < 6;
-    // this lane's word inside a dense 32 x 96 B output tile: row 4 (warp >> 2) + (lane >> 3) + 8 k
-    const int ooff = (4 * (warp >> 2) + (lane >> 3)) * 96 + (warp & 3) * 24 + wj * 4;
-    const uint32_t s_stage = smem_u32(smem), s_out = s_stage + kOffOut, s_bar = s_stage + kOffBar;
-    uint8_t* const outp = smem + kOffOut + ooff;
+    // this lane's word of patch k inside a dense 32 x 96 B out tile: row 4 warp + (lane >> 3), byte 24 k + 4 wj
+    uint8_t* const outp = smem + kOffOut + (4 * warp + (lane >> 3)) * (kTile * 3) + wj * 4;
 
-    const int n_items = (f1 - f0) * NV;
-    const int nbox = (tg.nrows + kBoxRows - 1) / kBoxRows;
-    const uint32_t tx_bytes = (uint32_t)(nbox * kBoxRows * PITCH);
-    int dst_x[NV];
+    int st = 0;
+    uint32_t ph = 0;
+    for (int n = 0; n < n_items; ++n) {
+        mbar_wait(s_full + st * 8, ph);
+        const uint8_t* buf = smem + st * stage_bytes;
+        uint32_t res[kPx];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) dst_x[v] = (a.view[v_begin + v].dst_x_offset + tg.x0) * 3;
-
-    auto issue = [&](int v, int f, int st) {  // thread 0: fetch the source rectangle of (frame f, view v) into stage st
-        const uint32_t bar = s_bar + st * 8;
-        const CUtensorMap* map = &tm.src[v_begin + v][PITCH == kPitchWide ? 1 : 0];
-        mbar_expect_tx(bar, tx_bytes);
-        for (int b = 0; b < nbox; ++b)
-            tma_load_3d(s_stage + st * kStageBytes + b * kBoxRows * PITCH, map, tg.bx0, tg.mny + b * kBoxRows, f, bar);
-    };
-
-    if (tid == 0) {
+        for (int k = 0; k < kPx; ++k)
+            res[k] = sample3<PITCH>(reinterpret_cast<const uint32_t*>(buf + pc.boff[k]), pc.sh[k], pc.W01[k], pc.W23[k]);
+        uint32_t word[kPx];
 #pragma unroll
-        for (int n = 0; n < kStages; ++n)
-            if (n < n_items) issue(n % NV, f0 + n / NV, n);
-    }
-
-    constexpr int U = (NV == 2) ? 6 : 3;
-    uint32_t it_parity = 0;  // U == 3: every stage is used once per outer iteration
-    for (int base = 0; base < n_items; base += U) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (base + u < n_items) {
-                const int st = u % kStages, v = u % NV;
-                const int f = f0 + (base + u) / NV;
-                const uint32_t parity = (U == 6) ? (uint32_t)(u / kStages) : it_parity;
-                mbar_wait(s_bar + st * 8, parity);
-
-                const uint8_t* buf = smem + st * kStageBytes;
-                uint32_t res[kPx];
-#pragma unroll
-                for (int k = 0; k < kPx; ++k)
-                    res[k] = sample3<PITCH>(reinterpret_cast<const uint32_t*>(buf + pc.boff[k]), pc.sh[k], pc.W01[k],
-                                            pc.W23[k]);
-#pragma unroll
-                for (int k = 0; k < kPx; ++k) {
-                    const uint32_t pa = __shfl_sync(0xffffffffu, res[k], p0c);
-                    const uint32_t pb = __shfl_sync(0xffffffffu, res[k], p1c);
-                    if (writer)
-                        *reinterpret_cast<uint32_t*>(outp + st * kOutTileBytes + k * 8 * 96) = __byte_perm(pa, pb, out_sel);
-                }
-                fence_proxy_async();
-                if (tid == 0) bulk_wait_read<1>();
-                __syncthreads();
-                if (tid == 0) {
-                    tma_store_3d(&tm.dst, dst_x[v], tg.y0, f, s_out + st * kOutTileBytes);
-                    bulk_commit();
-                    if (base + u + kStages < n_items) issue((u + kStages) % NV, f0 + (base + u + kStages) / NV, st);
-                }
-            }
+        for (int k = 0; k < kPx; ++k) {
+            const uint32_t pa = __shfl_sync(0xffffffffu, res[k], p0c);
+            const uint32_t pb = __shfl_sync(0xffffffffu, res[k], p1c);
+            word[k] = __byte_perm(pa, pb, out_sel);
         }
-        it_parity ^= 1u;
+        const int o = n & (kOutBufs - 1);
+        if (n >= kOutBufs) mbar_wait(s_oempty + o * 8, (uint32_t)(n / kOutBufs + 1) & 1u);  // store n - 4 has read out[o]
+        if (writer) {
+#pragma unroll
+            for (int k = 0; k < kPx; ++k) *reinterpret_cast<uint32_t*>(outp + o * kOutTileBytes + k * 24) = word[k];
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(s_ofull + o * 8);   // this warp's rows of item n are in out[o]
+            mbar_arrive(s_empty + st * 8);  // this warp is done with stage st
+        }
+        if (++st == S) { st = 0; ph ^= 1u; }
     }
-    if (tid == 0) bulk_wait_read<0>();  // shared memory must stay valid until the last store has read it
 }
 
 __global__ void __launch_bounds__(kThreads, 4)
@@ -258,7 +282,15 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
 #pragma unroll
-        for (int st = 0; st < kStages; ++st) mbar_init(smem_u32(smem + kOffBar) + st * 8, 1);
+        const uint32_t bars = smem_u32(smem + kOffBar);
+        for (int st = 0; st < kMaxStages; ++st) {
+            mbar_init(bars + st * 8, 1);                               // full: thread 0 + tx bytes
+            mbar_init(bars + (kMaxStages + st) * 8, kSamplers / 32);  // empty: one arrive per sampling warp
+        }
+        for (int o = 0; o < kOutBufs; ++o) {
+            mbar_init(bars + (2 * kMaxStages + o) * 8, kSamplers / 32);       // ofull: one arrive per sampling warp
+            mbar_init(bars + (2 * kMaxStages + kOutBufs + o) * 8, 1);         // oempty: the producer
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy (TMA)
     }
     const int tx = blockIdx.x % tp.tiles_x, ty = blockIdx.x / tp.tiles_x;
@@ -267,12 +299,15 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     const ViewArgs& mv = a.view[g];
     const int v_begin = g, v_end = a.share_map ? a.n_views : g + 1, nv = v_end - v_begin;
     const int f0 = blockIdx.z * a.frames_per_cta, f1 = min(a.n_frames, f0 + a.frames_per_cta);
-    const int lx = 8 * (warp & 3) + (lane & 7), ly = 4 * (warp >> 2) + (lane >> 3);  // pixel k: (lx, ly + 8 k)
-    const int i = x0 + lx;
+    const bool sampler = warp < kSamplers / 32;              // warp 8 = TMA producer: no pixels of its own
+    const int lx = lane & 7, ly = 4 * (warp & 7) + (lane >> 3);  // pixel k of this thread: (lx + 8 k, ly)
+    const int j = y0 + ly;
     const bool full_tile = (x0 + kTile <= a.W) && (y0 + kTile <= a.H);
 
     // ---- coordinates of this thread's 4 pixels ------------------------------------------------------------
     int sx[kPx], sy[kPx];
+#pragma unroll
+    for (int k = 0; k < kPx; ++k) sx[k] = sy[k] = 0;
     if (mv.map_kind == VR180_MAPSRC_ANALYTIC) {
         const vr180_chain_t& ch = mv.chain_idx ? chain1 : chain0;
         const StdChain& sc = tp.std[mv.chain_idx ? 1 : 0];
@@ -292,10 +327,9 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
             }
             __syncthreads();
             const bool lat_is_y = ch.ops[1].iparam != 0;
-            const double s_col = s_trig[lx], c_col = s_trig[32 + lx];
+            const double s_row = s_trig[64 + ly], c_row = s_trig[96 + ly];
             auto seed = [&](int k, ChainState& s) {
-                const int r = ly + 8 * k;
-                const double s_row = s_trig[64 + r], c_row = s_trig[96 + r];
+                const double s_col = s_trig[lx + 8 * k], c_col = s_trig[32 + lx + 8 * k];
                 s.mode = MODE_VEC3;
                 s.x = s.y = s.r = s.ux = s.uy = 0.0;
                 if (lat_is_y) {  // lat from the row, lon from the column
@@ -308,18 +342,25 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                     s.vz = mul_rn(c_col, c_row);
                 }
             };
-            if (sc.valid) {  // straight-line: the same op functions, in the same order, as the interpreter would run
+            if (!sampler) {
+            } else if (sc.valid) {  // straight-line: the same op functions, in the same order, as the interpreter would run
+                // instantiated once per chain so that R, the polynomial and the denormalisation are read with static
+                // constant-bank operands (no indexed LDC, no register copies)
+                auto std_eval = [&](const StdChain& c) {
 #pragma unroll
-                for (int k = 0; k < kPx; ++k) {
-                    ChainState s;
-                    seed(k, s);
-                    if (sc.has_rot) op_rot3(sc.R, s);
-                    if (sc.n_poly >= 0) op_poly(sc.poly, sc.n_poly, s);
-                    op_fisheye_dec(VR180_MAP_EQUIDISTANT, s);
-                    op_denormalize(sc.den, s);
-                    sx[k] = quantise(__double2float_rn(s.x));  // astype(float32) then cvRound(x * 32)
-                    sy[k] = quantise(__double2float_rn(s.y));
-                }
+                    for (int k = 0; k < kPx; ++k) {
+                        ChainState s;
+                        seed(k, s);
+                        if (c.has_rot) op_rot3(c.R, s);
+                        if (c.n_poly >= 0) op_poly(c.poly, c.n_poly, s);
+                        op_fisheye_dec(VR180_MAP_EQUIDISTANT, s);
+                        op_denormalize(c.den, s);
+                        sx[k] = quantise(__double2float_rn(s.x));  // astype(float32) then cvRound(x * 32)
+                        sy[k] = quantise(__double2float_rn(s.y));
+                    }
+                };
+                if (mv.chain_idx) std_eval(tp.std[1]);
+                else std_eval(tp.std[0]);
             } else {
 #pragma unroll 1
                 for (int k = 0; k < kPx; ++k) {
@@ -333,21 +374,21 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                         if (kk == k) { sx[kk] = qx; sy[kk] = qy; }
                 }
             }
-        } else {
+        } else if (sampler) {
 #pragma unroll 1
             for (int k = 0; k < kPx; ++k) {
                 double xs, ys;
-                eval_chain(ch, i, y0 + ly + 8 * k, xs, ys);
+                eval_chain(ch, x0 + lx + 8 * k, j, xs, ys);
                 const int qx = quantise(__double2float_rn(xs)), qy = quantise(__double2float_rn(ys));
 #pragma unroll
                 for (int kk = 0; kk < kPx; ++kk)
                     if (kk == k) { sx[kk] = qx; sy[kk] = qy; }
             }
         }
-    } else {
+    } else if (sampler) {
 #pragma unroll
         for (int k = 0; k < kPx; ++k) {
-            const int j = y0 + ly + 8 * k;
+            const int i = x0 + lx + 8 * k;
             sx[k] = sy[k] = (int)0x80000000;
             if (i < a.W && j < a.H) {
                 if (mv.map_kind == VR180_MAPSRC_FLOAT2) {
@@ -376,15 +417,17 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     mxx = __reduce_max_sync(0xffffffffu, mxx);
     mny = __reduce_min_sync(0xffffffffu, mny);
     mxy = __reduce_max_sync(0xffffffffu, mxy);
-    if (lane == 0) {
+    if (lane == 0 && sampler) {
         s_red[warp * 4 + 0] = mnx;
         s_red[warp * 4 + 1] = mxx;
         s_red[warp * 4 + 2] = mny;
         s_red[warp * 4 + 3] = mxy;
     }
     __syncthreads();
+    mnx = mny = INT_MAX;
+    mxx = mxy = INT_MIN;
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) {
+    for (int w = 0; w < kSamplers / 32; ++w) {
         mnx = min(mnx, s_red[w * 4 + 0]);
         mxx = max(mxx, s_red[w * 4 + 1]);
         mny = min(mny, s_red[w * 4 + 2]);
@@ -400,11 +443,11 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     (void)v0;
 
     if (!fast) {  // per-pixel gather from global memory with full border handling (rare tiles)
-        if (i < a.W) {
+        if (sampler && j < a.H) {
 #pragma unroll
             for (int k = 0; k < kPx; ++k) {
-                const int j = y0 + ly + 8 * k;
-                if (j < a.H) {
+                const int i = x0 + lx + 8 * k;
+                if (i < a.W) {
                     for (int f = f0; f < f1; ++f) {
                         uint8_t* drow = a.dst + (long long)f * a.dst_frame_stride + (long long)j * a.dst_pitch;
                         for (int v = v_begin; v < v_end; ++v) {
@@ -537,14 +580,12 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
     for (int v = 0; v < a0.n_views; ++v) {
         const ViewArgs& vw = a0.view[v];
         for (int w = 0; w < 2; ++w)
-            if (!encode_u8_3d(&tm.src[v][w], vw.src, (long long)vw.cols * 3, vw.rows, a0.n_frames, vw.pitch, vw.frame_stride,
-                              w ? kPitchWide : kPitchNarrow, kBoxRows))
-                return VR180_ERR_UNSUPPORTED;
+            for (int r = 0; r < kRowSizes; ++r)
+                if (!encode_u8_3d(&tm.src[v][w][r], vw.src, (long long)vw.cols * 3, vw.rows, a0.n_frames, vw.pitch,
+                                  vw.frame_stride, w ? kPitchWide : kPitchNarrow, kRowsMin + r * kRowsStep))
+                    return VR180_ERR_UNSUPPORTED;
     }
-    if (a0.n_views == 1) {
-        tm.src[1][0] = tm.src[0][0];
-        tm.src[1][1] = tm.src[0][1];
-    }
+    if (a0.n_views == 1) memcpy(&tm.src[1], &tm.src[0], sizeof(tm.src[0]));
     if (!encode_u8_3d(&tm.dst, a0.dst, a0.dst_pitch, a0.H, a0.n_frames, a0.dst_pitch, a0.dst_frame_stride, kTile * 3, kTile))
         return VR180_ERR_UNSUPPORTED;
 
