@@ -52,6 +52,8 @@ WORKLOADS = {
     "5k7_lut_linear": dict(n=2880, interp=1, tuple_=False, chain="base", src="lut_fixed", radius="fixed", pairs=32,
                            desc="batched 5.7K pairs (2x2880^2 -> 5760x2880), cached fixed-point LUT, INTER_LINEAR "
                                 "[BASELINE configs[3]]"),
+    "8k_cubic_fixed": dict(n=4096, interp=2, tuple_=False, chain="base", src="analytic", radius="fixed", pairs=16,
+                           desc="batched 8K pairs, base chain, fused analytic, INTER_CUBIC, fixed radius"),
     "8k_cubic_auto": dict(n=4096, interp=2, tuple_=False, chain="base", src="analytic", radius="auto", pairs=16,
                           desc="batched 8K pairs, base chain, fused analytic + get_radius per frame consumed on device, "
                                "INTER_CUBIC [BASELINE configs[4]]"),

@@ -307,6 +307,41 @@ def test_sbs_warper_per_eye_tuple_and_auto_radius():
         assert np.array_equal(got[f], want), f
 
 
+@pytest.mark.parametrize("interp", [1, 2])
+@pytest.mark.parametrize("per_eye", [False, True])
+def test_tiled_pipeline_ring_wraparound_and_source_edges(interp, per_eye):
+    """Stress of the tiled TMA pipeline (csrc/tiled.cu): an odd, long batch (stage ring, out-buffer ring and
+    mbarrier phases wrap several times), a radius larger than the source so that many tiles straddle the source
+    edge (TMA zero fill == BORDER_CONSTANT 0), tiles fully outside, partial edge tiles (output 200 x 104 is not a
+    multiple of the 32 x 32 / 32 x 16 tiles), shared map (2 views per CTA) and per-eye maps (1 view per CTA)."""
+    import torch
+
+    n, hin, win, wout, hout = 23, 192, 224, 200, 104
+    ql, qr = V.from_rotation_vector([0.03, -0.02, 0.05]), V.from_rotation_vector([-0.03, 0.02, -0.05])
+    mk = lambda q: (V.EquirectangularEncoder() * V.Euclidean3DRotator(q) * V.PolynomialScaler([0, 1, 0.05])  # noqa: E731
+                    * V.FisheyeDecoder("equidistant"))
+    t = (mk(ql), mk(qr)) if per_eye else mk(ql)
+    rng = np.random.default_rng(7)
+    ln = rng.integers(0, 256, (n, hin, win, 3), dtype=np.uint8)  # no black surround: edges carry signal
+    rn = rng.integers(0, 256, (n, hin, win, 3), dtype=np.uint8)
+    left, right = torch.from_numpy(ln).cuda(), torch.from_numpy(rn).cuda()
+    radius = 150.0  # > min(hin, win) / 2: the footprint leaves the source on every side
+    wp = V.SbsWarper(t, size_input=(hin, win), size_output=(wout, hout), interpolation=interp, radius=radius)
+    got = wp(left, right).cpu().numpy()
+
+    def omap(q):
+        ops = [("equirect_enc", True), ("rot3", chain_np.quat_to_matrix(*q.components).ravel().tolist()),
+               ("poly", [0, 1, 0.05]), ("fisheye_dec", "equidistant")]
+        return chain_np.get_map(ops, radius=radius, size_input=(hin, win), size_output=(wout, hout))
+
+    ml = omap(ql)
+    mr = omap(qr) if per_eye else ml
+    for f in range(n):
+        want = np.concatenate([cv2.remap(ln[f], ml[0], ml[1], interpolation=interp),
+                               cv2.remap(rn[f], mr[0], mr[1], interpolation=interp)], axis=1)
+        assert np.array_equal(got[f], want), (interp, per_eye, f, int((got[f] != want).sum()))
+
+
 # ---------------------------------------------------------------------------------------------------------
 # (6) full BASELINE sizes through size-independent properties
 # ---------------------------------------------------------------------------------------------------------

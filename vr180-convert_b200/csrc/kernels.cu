@@ -20,8 +20,8 @@ namespace vr180 {
 // ---------------------------------------------------------------------------------------------------------
 // weight tables (device copies, one per device, filled on first use)
 // ---------------------------------------------------------------------------------------------------------
-__device__ short g_tab_cubic[1024 * 16];
-__device__ short g_tab_lanczos[1024 * 64];
+__device__ __align__(16) short g_tab_cubic[1024 * 16];
+__device__ __align__(16) short g_tab_lanczos[1024 * 64];
 
 static std::once_flag g_tab_host_once;
 static std::vector<int16_t> g_tab_cubic_host, g_tab_lanczos_host;
@@ -273,7 +273,9 @@ int launch_remap(const vr180_remap_params_t* p, cudaStream_t st) {
     // fast path: tiled, smem-staged kernel (tiled.cu); VR180_DISABLE_TILED=1 forces the generic gather (A/B tests)
     static const bool tiled_off = [] { const char* e = getenv("VR180_DISABLE_TILED"); return e && *e == '1'; }();
     if (!tiled_off) {
-        const int rc = launch_remap_tiled(a, C, interp, *chains[0], *chains[1], st);
+        const short* tab_cubic = nullptr;
+        if (interp == VR180_INTER_CUBIC) VR180_CUDA(cudaGetSymbolAddress((void**)&tab_cubic, g_tab_cubic));
+        const int rc = launch_remap_tiled(a, C, interp, *chains[0], *chains[1], tab_cubic, st);
         if (rc != VR180_ERR_UNSUPPORTED) return rc;
     }
 

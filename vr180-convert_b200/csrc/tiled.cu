@@ -1,31 +1,33 @@
-// tiled.cu -- the tiled fast path of the fused warp: uint8 x 3 channels, INTER_LINEAR, BORDER_CONSTANT (0).
+// tiled.cu -- the tiled fast path of the fused warp: uint8 x 3 channels, INTER_LINEAR or INTER_CUBIC,
+// BORDER_CONSTANT (0).
 //
 // Replaces cv.remap per eye + np.concatenate (/root/reference/src/vr180_convert/remapper.py:388-398, :518) and,
 // for MAPSRC_ANALYTIC, get_map (remapper.py:23-59) for a batch of frames that share their maps (the reference's
 // apply(): ONE map, N images, remapper.py:381-398).
 //
-// One CTA owns a 32x32 tile of one eye's output (or of both eyes when they share a map) for every frame of its
-// frame chunk:
-//   prologue   coordinates of the tile's 1024 pixels, once: analytic chain in float64 (row / column sincos of the
+// One CTA owns a tile of one eye's output (32 x 32 bilinear, 32 x 16 bicubic; of both eyes when they share a map)
+// for every frame of its frame chunk:
+//   prologue   coordinates of the tile's pixels, once: analytic chain in float64 (row / column sincos of the
 //              Normalize + EquirectangularEncoder prefix are separable and computed 64x per tile instead of
 //              2048x; the standard chain shape runs as straight-line code, anything else through the op
 //              interpreter of chain.cuh), or float32 maps, or the fixed-point LUT; quantised exactly like
-//              cv::remap (sampler.cuh); per pixel only {smem offset of tap00, byte shift, packed bilinear
+//              cv::remap (sampler.cuh); per pixel only {smem offset of the first tap, byte shift, packed integer
 //              weights} stay in registers.
 //   bbox       block-wide min / max of the integer source coordinates -> the tile's source rectangle.
-//   pipeline   for every (frame, eye) item the source rectangle is fetched by TMA (cp.async.bulk.tensor.3d over the
-//              (bytes, rows, frames) view of the source batch, boxes of 8 rows, completion on an mbarrier), 3
-//              stages deep: the loads of items k+1 .. k+3 are in flight while item k is sampled.  TMA's
-//              out-of-bounds zero fill IS BORDER_CONSTANT(0), so tiles that straddle the source edge stay on the
-//              fast path.  No LSU instruction touches the source (the previous cp.async version spent 23 % of its
-//              shared-memory wavefronts on LDGSTS, profiles/r1_v4_*).
-//   sampling   a warp samples an 8 x 4 pixel patch: 6 LDS.32 per pixel (2 rows x 12 bytes), funnel shifts to
-//              byte-align, PRMT to pair the taps, 2 x dp2a (16-bit weight x 8-bit pixel) per channel:
-//                  (sum_t w_t p_t + 512) >> 10  ==  (sum_t 64 w_t p_t + 32768) >> 16
-//              so the result is byte 2 of the dp2a chain and is packed with two PRMTs.
-//   store      each patch row's 8 pixels x 3 bytes are re-packed with two shuffles into 6 words of a dense 32 x 96
-//              byte output tile in shared memory; one elected thread writes the tile into the eye's half of the
-//              SBS frame with a TMA store (full 32-byte sectors, no STG).
+//   pipeline   for every (frame, eye) item the source rectangle is fetched by ONE TMA box load
+//              (cp.async.bulk.tensor.3d over the (bytes, rows, frames) view of the source batch, completion on an
+//              mbarrier) into a ring of stages sized for this tile; a dedicated producer warp runs the loads
+//              S - 2 items ahead.  TMA's out-of-bounds zero fill IS BORDER_CONSTANT(0), so tiles that straddle the
+//              source edge stay on the fast path.  No LSU instruction touches the source in global memory.
+//   sampling   a warp samples an 8 x 4 pixel patch per step.  Bilinear: 6 LDS.32 per pixel (2 rows x 12 bytes),
+//              funnel shifts to byte-align, PRMT to pair the taps, 2 x dp2a (16-bit weight x 8-bit pixel) per
+//              channel:  (sum_t w_t p_t + 512) >> 10  ==  (sum_t 64 w_t p_t + 32768) >> 16, i.e. byte 2 of the
+//              dp2a chain.  Bicubic: 4 rows x 16-byte windows, the pixel's 16 int16 table weights (OpenCV's
+//              1024 x 16 table, tables.cuh) live in 8 registers, 2 x dp2a (s16 x u8) per channel and row,
+//              clip((acc + 16384) >> 15).
+//   store      each patch row's 8 pixels x 3 bytes are re-packed with two shuffles into 6 words of a dense output
+//              tile in shared memory; the producer writes the tile into the eye's half of the SBS frame with one
+//              TMA store (full 32-byte sectors, no STG).
 // Tiles whose footprint is unbounded (NaN / huge coordinates) or exceeds the staging buffer, and partial edge
 // tiles, take the per-pixel global-memory gather of sampler.cuh inside the same kernel.
 #include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint
@@ -40,26 +42,23 @@
 namespace vr180 {
 namespace tiled {
 
-constexpr int kTile = 32;       // output tile edge
-constexpr int kPx = 4;          // pixels per thread.  A warp covers an 8 x 4 pixel patch per k (lane & 7 = column,
+constexpr int kTileW = 32;      // output tile width; a warp covers an 8 x 4 pixel patch per step (lane & 7 = column,
                                 // lane >> 3 = row): its source footprint is a compact 2-D patch whatever the local
-                                // direction of the map, which keeps the tap loads (nearly) free of bank conflicts;
-                                // warp w owns output rows 4 w .. 4 w + 3 of the tile, k = patch column (8 px each)
+                                // direction of the map, which keeps the tap loads (nearly) free of bank conflicts
 constexpr int kSamplers = 256;  // 8 sampling warps
 constexpr int kThreads = kSamplers + 32;  // + the TMA producer warp
 constexpr int kMaxStages = 8;   // ring depth is chosen per tile: kStageArea / (bytes of the tile's source rectangle)
-constexpr int kRowsMin = 32, kRowsStep = 8, kRowSizes = 5;  // TMA load box heights: 32, 40, 48, 56, 64 rows
+constexpr int kRowsStep = 8, kRowSizes = 5;  // TMA load box heights: Mode::kRowsMin + 8 r, r < 5
 constexpr int kPitchNarrow = 160, kPitchWide = 224;  // staged row pitch = TMA box width (bytes).  40 / 56 words =
                                 // +8 / -8 banks per row, so the <= 8-word row segments of a patch's 4 source rows
                                 // fall into disjoint banks
-constexpr int kMaxRows = 64;
 constexpr int kStageArea = 40960;  // >= 2 stages of the largest admissible rectangle (64 rows x 224 B)
-constexpr int kOutTileBytes = kTile * kTile * 3;    // dense 32 x 96 B output tile = one TMA store box
-constexpr int kOutBufs = 4;                         // power of two
+constexpr int kOutBufs = 4;        // power of two
+constexpr int kOutArea = kOutBufs * 32 * kTileW * 3;
 constexpr int kOffOut = kStageArea;
-constexpr int kOffTrig = kOffOut + kOutBufs * kOutTileBytes;
+constexpr int kOffTrig = kOffOut + kOutArea;
 constexpr int kOffRed = kOffTrig + 4 * 32 * 8;
-constexpr int kOffBar = kOffRed + 8 * 4 * 4;        // full[kMaxStages], empty[kMaxStages], ofull[kOutBufs], oempty[kOutBufs]
+constexpr int kOffBar = kOffRed + 8 * 4 * 4;  // full[kMaxStages], empty[kMaxStages], ofull[kOutBufs], oempty[kOutBufs]
 constexpr int kSmemBytes = kOffBar + (2 * kMaxStages + 2 * kOutBufs) * 8;
 
 // The standard chain shape, lowered once on the host (see match_std_chain):
@@ -76,13 +75,14 @@ struct StdChain {
 struct TiledParams {
     int tiles_x;
     int sep_prefix;  // generic chains only: ops[0..1] = Normalize, EquirectangularEncoder
+    const short* tab;  // bicubic: OpenCV's 1024 x 16 int16 weight table (device)
     StdChain std[2];
 };
 
 // TMA descriptors of one launch (kernel parameter; the TMA unit reads them from the parameter bank).
 struct alignas(64) TmaMaps {
-    CUtensorMap src[2][2][kRowSizes];  // [view][0: 160-byte, 1: 224-byte boxes][box rows 32 + 8 r]: uint8 (cols * 3, rows, frames)
-    CUtensorMap dst;                   // uint8 (dst_pitch, H, frames), box (96, 32, 1)
+    CUtensorMap src[2][2][kRowSizes];  // [view][0: 160-byte, 1: 224-byte boxes][box rows kRowsMin + 8 r]: uint8 (cols * 3, rows, frames)
+    CUtensorMap dst;                   // uint8 (dst_pitch, H, frames), box (96, tile height, 1)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,75 +127,134 @@ __device__ __forceinline__ void bulk_wait_read() {  // all but the N newest bulk
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
-// Packed bilinear weights of one pixel as 16-bit lanes: W01 = {64 w00, 64 w01}, W23 = {64 w10, 64 w11}.
-// w00 = 1024 (ax = ay = 0, all other weights 0) is encoded as 65535: (65535 p + 32768) >> 16 is still exactly p.
-__device__ __forceinline__ void pack_weights(int ax, int ay, uint32_t& W01, uint32_t& W23) {
-    const int w00 = (32 - ax) * (32 - ay), w01 = ax * (32 - ay), w10 = (32 - ax) * ay, w11 = ax * ay;
-    W01 = (uint32_t)min(64 * w00, 65535) | ((uint32_t)(64 * w01) << 16);
-    W23 = (uint32_t)(64 * w10) | ((uint32_t)(64 * w11) << 16);
+__device__ __forceinline__ uint32_t dp2a_lo_su(uint32_t w, uint32_t px, uint32_t acc) {  // s16 x u8, bytes 0..1
+    uint32_t d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(acc));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi_su(uint32_t w, uint32_t px, uint32_t acc) {  // s16 x u8, bytes 2..3
+    uint32_t d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(acc));
+    return d;
 }
 
-// One output pixel from the staged tile (r0 = aligned window of tap row 0): the three result bytes [c0 c1 c2 0].
-template <int PITCH>
-__device__ __forceinline__ uint32_t sample3(const uint32_t* __restrict__ r0, int sh, uint32_t W01, uint32_t W23) {
-    const uint32_t* r1 = r0 + PITCH / 4;
-    // the 6 tap bytes start at byte sh / 8 of the window: only an offset of 3 reaches into the third word, so 3/4 of
-    // the lanes skip that load (fewer active lanes = fewer bank conflicts)
-    const bool third = sh == 24;
-    const uint32_t a0 = r0[0], a1 = r0[1], a2 = third ? r0[2] : 0u;
-    const uint32_t b0 = r1[0], b1 = r1[1], b2 = third ? r1[2] : 0u;
-    // byte-align: lo = [c0 c1 c2 c0'], hi = [c1' c2' . .]  (primed = the pixel at ix + 1)
-    const uint32_t r0lo = __funnelshift_r(a0, a1, sh), r0hi = __funnelshift_r(a1, a2, sh);
-    const uint32_t r1lo = __funnelshift_r(b0, b1, sh), r1hi = __funnelshift_r(b1, b2, sh);
-    const uint32_t q0 = __byte_perm(r0lo, r1lo, 0x7430);  // channel 0: [p00 p01 | p10 p11]
-    const uint32_t t0 = __byte_perm(r0lo, r0hi, 0x5241);  // row 0: [c1 c1' | c2 c2']
-    const uint32_t t1 = __byte_perm(r1lo, r1hi, 0x5241);  // row 1
-    // (sum_t w_t p_t + 512) >> 10 == (sum_t 64 w_t p_t + 32768) >> 16: the result is byte 2 of s (s < 2^24)
-    const uint32_t s0 = __dp2a_hi(W23, q0, __dp2a_lo(W01, q0, 32768u));
-    const uint32_t s1 = __dp2a_lo(W23, t1, __dp2a_lo(W01, t0, 32768u));
-    const uint32_t s2 = __dp2a_hi(W23, t1, __dp2a_hi(W01, t0, 32768u));
-    return __byte_perm(__byte_perm(s0, s1, 0x0062), s2, 0x7610);
-}
-
-struct PixelConst {  // per output pixel, constant over the frames of the batch
-    int boff[kPx];      // byte offset (4-aligned) of the 12-byte tap window of row 0 inside a stage buffer
-    int sh[kPx];        // 8 * (tap00 byte offset & 3)
-    uint32_t W01[kPx], W23[kPx];
+// ---- interpolation modes -------------------------------------------------------------------------------------
+// A mode fixes: pixels per thread (the per-pixel constants must stay in registers across the frames of the batch),
+// the tile height, the tap footprint (taps start kLo pixels / rows before the integer coordinate and end kHi after
+// it), the per-pixel constants and the sampling of one pixel from the staged rectangle.
+struct Linear {
+    static constexpr int kPx = 4, kTileH = 32, kLo = 0, kHi = 1, kRowsMin = 32, kInterp = VR180_INTER_LINEAR;
+    struct Pixel {  // constant over the frames of the batch
+        int boff;          // byte offset (4-aligned) of the 12-byte tap window of row 0 inside a stage buffer
+        int sh;            // 8 * (tap00 byte offset & 3)
+        uint32_t W01, W23; // 16-bit lanes {64 w00, 64 w01}, {64 w10, 64 w11}
+    };
+    // w00 = 1024 (ax = ay = 0, all other weights 0) is encoded as 65535: (65535 p + 32768) >> 16 is still exactly p.
+    __device__ static __forceinline__ void weights(Pixel& p, int ax, int ay, const short*) {
+        const int w00 = (32 - ax) * (32 - ay), w01 = ax * (32 - ay), w10 = (32 - ax) * ay, w11 = ax * ay;
+        p.W01 = (uint32_t)min(64 * w00, 65535) | ((uint32_t)(64 * w01) << 16);
+        p.W23 = (uint32_t)(64 * w10) | ((uint32_t)(64 * w11) << 16);
+    }
+    // One output pixel from the staged rectangle: the three result bytes [c0 c1 c2 0].
+    template <int PITCH>
+    __device__ static __forceinline__ uint32_t sample(const uint8_t* buf, const Pixel& p) {
+        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(buf + p.boff);
+        const uint32_t* r1 = r0 + PITCH / 4;
+        const int sh = p.sh;
+        // the 6 tap bytes start at byte sh / 8 of the window: only an offset of 3 reaches into the third word, so
+        // 3/4 of the lanes skip that load (fewer active lanes = fewer bank conflicts)
+        const bool third = sh == 24;
+        const uint32_t a0 = r0[0], a1 = r0[1], a2 = third ? r0[2] : 0u;
+        const uint32_t b0 = r1[0], b1 = r1[1], b2 = third ? r1[2] : 0u;
+        // byte-align: lo = [c0 c1 c2 c0'], hi = [c1' c2' . .]  (primed = the pixel at ix + 1)
+        const uint32_t r0lo = __funnelshift_r(a0, a1, sh), r0hi = __funnelshift_r(a1, a2, sh);
+        const uint32_t r1lo = __funnelshift_r(b0, b1, sh), r1hi = __funnelshift_r(b1, b2, sh);
+        const uint32_t q0 = __byte_perm(r0lo, r1lo, 0x7430);  // channel 0: [p00 p01 | p10 p11]
+        const uint32_t t0 = __byte_perm(r0lo, r0hi, 0x5241);  // row 0: [c1 c1' | c2 c2']
+        const uint32_t t1 = __byte_perm(r1lo, r1hi, 0x5241);  // row 1
+        // (sum_t w_t p_t + 512) >> 10 == (sum_t 64 w_t p_t + 32768) >> 16: the result is byte 2 of s (s < 2^24)
+        const uint32_t s0 = __dp2a_hi(p.W23, q0, __dp2a_lo(p.W01, q0, 32768u));
+        const uint32_t s1 = __dp2a_lo(p.W23, t1, __dp2a_lo(p.W01, t0, 32768u));
+        const uint32_t s2 = __dp2a_hi(p.W23, t1, __dp2a_hi(p.W01, t0, 32768u));
+        return __byte_perm(__byte_perm(s0, s1, 0x0062), s2, 0x7610);
+    }
 };
+
+struct Cubic {
+    static constexpr int kPx = 2, kTileH = 16, kLo = 1, kHi = 2, kRowsMin = 16, kInterp = VR180_INTER_CUBIC;
+    struct Pixel {
+        int boff;       // byte offset (4-aligned) of the 16-byte window of tap row 0 (iy - 1), first tap ix - 1
+        int sh;
+        uint32_t w[8];  // itab[ay][ax][ky][kx] as int16 pairs: w[2 ky] = {kx 0, kx 1}, w[2 ky + 1] = {kx 2, kx 3}
+    };
+    __device__ static __forceinline__ void weights(Pixel& p, int ax, int ay, const short* tab) {
+        const uint4* t = reinterpret_cast<const uint4*>(tab + ((ay << 5) | ax) * 16);
+        const uint4 lo = __ldg(t), hi = __ldg(t + 1);
+        p.w[0] = lo.x; p.w[1] = lo.y; p.w[2] = lo.z; p.w[3] = lo.w;
+        p.w[4] = hi.x; p.w[5] = hi.y; p.w[6] = hi.z; p.w[7] = hi.w;
+    }
+    template <int PITCH>
+    __device__ static __forceinline__ uint32_t sample(const uint8_t* buf, const Pixel& p) {
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(buf + p.boff);
+        const int sh = p.sh;
+        uint32_t acc0 = 16384u, acc1 = 16384u, acc2 = 16384u;  // + 1 << 14 before the >> 15
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky, r += PITCH / 4) {
+            const uint32_t a0 = r[0], a1 = r[1], a2 = r[2], a3 = r[3];
+            // byte-align the 12 tap bytes (taps t0..t3, channels 0..2):
+            //   A0 = [t0c0 t0c1 t0c2 t1c0]  A1 = [t1c1 t1c2 t2c0 t2c1]  A2 = [t2c2 t3c0 t3c1 t3c2]
+            const uint32_t A0 = __funnelshift_r(a0, a1, sh), A1 = __funnelshift_r(a1, a2, sh),
+                           A2 = __funnelshift_r(a2, a3, sh);
+            const uint32_t q0 = __byte_perm(__byte_perm(A0, A1, 0x0630), A2, 0x5210);  // [t0c0 t1c0 t2c0 t3c0]
+            const uint32_t q1 = __byte_perm(__byte_perm(A0, A1, 0x0741), A2, 0x6210);  // [t0c1 t1c1 t2c1 t3c1]
+            const uint32_t q2 = __byte_perm(__byte_perm(A0, A1, 0x0052), A2, 0x7410);  // [t0c2 t1c2 t2c2 t3c2]
+            const uint32_t w01 = p.w[2 * ky], w23 = p.w[2 * ky + 1];
+            acc0 = dp2a_hi_su(w23, q0, dp2a_lo_su(w01, q0, acc0));
+            acc1 = dp2a_hi_su(w23, q1, dp2a_lo_su(w01, q1, acc1));
+            acc2 = dp2a_hi_su(w23, q2, dp2a_lo_su(w01, q2, acc2));
+        }
+        const int c0 = min(max((int)acc0 >> 15, 0), 255), c1 = min(max((int)acc1 >> 15, 0), 255),
+                  c2 = min(max((int)acc2 >> 15, 0), 255);
+        return (uint32_t)c0 | ((uint32_t)c1 << 8) | ((uint32_t)c2 << 16);
+    }
+};
+
 struct TileGeom {
     int nrows;          // source rows of the tile's rectangle
-    int bx0, mny;       // first source byte column (16-aligned, may be negative) and first source row
+    int bx0, ry0;       // first source byte column (16-aligned, may be negative) and first source row
     int x0, y0;         // output tile origin
 };
 
 // The frame loop of one tile.  Items are (frame, view) pairs in frame-major order.  NV = views sampled with this
 // CTA's coordinates (2 when both eyes share the map).
 //
-// Warp-specialised: warps 0-7 sample (4 output rows each), lane 0 of warp 8 drives the TMA unit and nothing else,
-// so no sampling warp ever blocks on a copy.  TMA work is kept to TWO operations per item (one load box = the whole
-// source rectangle, one store box = the whole 32 x 96 B output tile): a version with 5 load boxes + 8 per-warp
-// store boxes per item measured TMA-issue bound (~50 clk per operation, profiles/r1_v7_*).
+// Warp-specialised: warps 0-7 sample, lane 0 of warp 8 drives the TMA unit and nothing else, so no sampling warp
+// ever blocks on a copy.  TMA work is kept to TWO operations per item (one load box = the whole source rectangle,
+// one store box = the whole output tile): a version with 5 load boxes + 8 per-warp store boxes per item measured
+// TMA-issue bound (~50 clk per operation, profiles/r1_v7_*).
 //
 // The staging area is a ring of S stages of exactly the tile's footprint (box rows x PITCH bytes), so a typical
-// tile (40 rows x 160 B = 6.4 KB) gets S = 6 and the loads run D = S - 2 items ahead of the sampling.
+// bilinear tile (40 rows x 160 B = 6.4 KB) gets S = 6 and the loads run D = S - 2 items ahead of the sampling.
 // No CTA-wide barrier; four kinds of mbarrier:
 //   full[s]    (1 + tx bytes)  the box of the item in stage s has landed; the sampling warps wait on it
 //   empty[s]   (8)             one arrive per sampling warp when it is done reading stage s; the producer waits
 //                              before re-filling (with D = S - 2 that is the stage of item n - 2)
-//   ofull[o]   (8)             one arrive per sampling warp when its 4 rows of the output tile are in out buffer o
+//   ofull[o]   (8)             one arrive per sampling warp when its rows of the output tile are in out buffer o
 //                              (4 deep); the producer waits, then issues the TMA store
 //   oempty[o]  (1)             the producer arrives when the store that last used out buffer o has finished reading
 //                              it (bulk wait_group.read); the sampling warps wait before rewriting it (item n - 4)
-template <int NV, int PITCH>
+template <class M, int NV, int PITCH>
 __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm, int v_begin, int f0, int f1,
-                                           const PixelConst& pc, const TileGeom& tg, uint8_t* smem) {
+                                           const typename M::Pixel (&pc)[M::kPx], const TileGeom& tg, uint8_t* smem,
+                                           int band, int cg) {
+    constexpr int kOutTileBytes = M::kTileH * kTileW * 3;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s_stage = smem_u32(smem), s_full = s_stage + kOffBar, s_empty = s_full + kMaxStages * 8;
     const uint32_t s_ofull = s_empty + kMaxStages * 8, s_oempty = s_ofull + kOutBufs * 8, s_out = s_stage + kOffOut;
 
     const int n_items = (f1 - f0) * NV;
-    const int rsel = tg.nrows <= kRowsMin ? 0 : (tg.nrows - kRowsMin + kRowsStep - 1) / kRowsStep;
-    const int stage_bytes = (kRowsMin + rsel * kRowsStep) * PITCH;  // multiple of 128
+    const int rsel = tg.nrows <= M::kRowsMin ? 0 : (tg.nrows - M::kRowsMin + kRowsStep - 1) / kRowsStep;
+    const int stage_bytes = (M::kRowsMin + rsel * kRowsStep) * PITCH;  // multiple of 128
     const int S = min(kMaxStages, kStageArea / stage_bytes), D = S <= 3 ? S - 1 : S - 2;
 
     if (warp == kSamplers / 32) {  // ---- producer ----
@@ -209,7 +268,7 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
             const int v = (NV == 2) ? (p_item & 1) : 0, f = f0 + ((NV == 2) ? (p_item >> 1) : p_item);
             if (p_use > 0) mbar_wait(s_empty + p_stage * 8, (uint32_t)(p_use + 1) & 1u);
             mbar_expect_tx(bar, (uint32_t)stage_bytes);
-            tma_load_3d(s_stage + p_stage * stage_bytes, map0 + v * (2 * kRowSizes), tg.bx0, tg.mny, f, bar);
+            tma_load_3d(s_stage + p_stage * stage_bytes, map0 + v * (2 * kRowSizes), tg.bx0, tg.ry0, f, bar);
             ++p_item;
             if (++p_stage == S) { p_stage = 0; ++p_use; }
         };
@@ -236,21 +295,20 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     const uint32_t out_sel = sub == 0 ? 0x4210u : (sub == 1 ? 0x5421u : 0x6542u);
     const int p0c = (lane & 24) + min(p0, 7), p1c = (lane & 24) + min(p0 + 1, 7);
     const bool writer = wj < 6;
-    // this lane's word of patch k inside a dense 32 x 96 B out tile: row 4 warp + (lane >> 3), byte 24 k + 4 wj
-    uint8_t* const outp = smem + kOffOut + (4 * warp + (lane >> 3)) * (kTile * 3) + wj * 4;
+    // this lane's word of patch k inside the dense out tile: row 4 band + (lane >> 3), byte 24 (kPx cg + k) + 4 wj
+    uint8_t* const outp = smem + kOffOut + (4 * band + (lane >> 3)) * (kTileW * 3) + M::kPx * cg * 24 + wj * 4;
 
     int st = 0;
     uint32_t ph = 0;
     for (int n = 0; n < n_items; ++n) {
         mbar_wait(s_full + st * 8, ph);
         const uint8_t* buf = smem + st * stage_bytes;
-        uint32_t res[kPx];
+        uint32_t res[M::kPx];
 #pragma unroll
-        for (int k = 0; k < kPx; ++k)
-            res[k] = sample3<PITCH>(reinterpret_cast<const uint32_t*>(buf + pc.boff[k]), pc.sh[k], pc.W01[k], pc.W23[k]);
-        uint32_t word[kPx];
+        for (int k = 0; k < M::kPx; ++k) res[k] = M::template sample<PITCH>(buf, pc[k]);
+        uint32_t word[M::kPx];
 #pragma unroll
-        for (int k = 0; k < kPx; ++k) {
+        for (int k = 0; k < M::kPx; ++k) {
             const uint32_t pa = __shfl_sync(0xffffffffu, res[k], p0c);
             const uint32_t pb = __shfl_sync(0xffffffffu, res[k], p1c);
             word[k] = __byte_perm(pa, pb, out_sel);
@@ -259,7 +317,7 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
         if (n >= kOutBufs) mbar_wait(s_oempty + o * 8, (uint32_t)(n / kOutBufs + 1) & 1u);  // store n - 4 has read out[o]
         if (writer) {
 #pragma unroll
-            for (int k = 0; k < kPx; ++k) *reinterpret_cast<uint32_t*>(outp + o * kOutTileBytes + k * 24) = word[k];
+            for (int k = 0; k < M::kPx; ++k) *reinterpret_cast<uint32_t*>(outp + o * kOutTileBytes + k * 24) = word[k];
         }
         fence_proxy_async();
         __syncwarp();
@@ -271,40 +329,44 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     }
 }
 
+template <class M>
 __global__ void __launch_bounds__(kThreads, 4)
 k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_chain_t chain0,
              const __grid_constant__ vr180_chain_t chain1, const __grid_constant__ TiledParams tp,
              const __grid_constant__ TmaMaps tm) {
+    constexpr int kPx = M::kPx;
+    constexpr int kWarpsPerBand = 4 / kPx;  // a band = 4 output rows x 32 columns = 4 / kPx warps of 8 kPx columns
     extern __shared__ __align__(1024) uint8_t smem[];
     double* s_trig = reinterpret_cast<double*>(smem + kOffTrig);  // [4][32]
     int* s_red = reinterpret_cast<int*>(smem + kOffRed);          // [8][4]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-#pragma unroll
         const uint32_t bars = smem_u32(smem + kOffBar);
         for (int st = 0; st < kMaxStages; ++st) {
-            mbar_init(bars + st * 8, 1);                               // full: thread 0 + tx bytes
+            mbar_init(bars + st * 8, 1);                               // full: the producer + tx bytes
             mbar_init(bars + (kMaxStages + st) * 8, kSamplers / 32);  // empty: one arrive per sampling warp
         }
         for (int o = 0; o < kOutBufs; ++o) {
-            mbar_init(bars + (2 * kMaxStages + o) * 8, kSamplers / 32);       // ofull: one arrive per sampling warp
-            mbar_init(bars + (2 * kMaxStages + kOutBufs + o) * 8, 1);         // oempty: the producer
+            mbar_init(bars + (2 * kMaxStages + o) * 8, kSamplers / 32);  // ofull: one arrive per sampling warp
+            mbar_init(bars + (2 * kMaxStages + kOutBufs + o) * 8, 1);    // oempty: the producer
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy (TMA)
     }
     const int tx = blockIdx.x % tp.tiles_x, ty = blockIdx.x / tp.tiles_x;
-    const int x0 = tx * kTile, y0 = ty * kTile;
+    const int x0 = tx * kTileW, y0 = ty * M::kTileH;
     const int g = blockIdx.y;  // map group: the view whose coordinates drive this CTA
     const ViewArgs& mv = a.view[g];
     const int v_begin = g, v_end = a.share_map ? a.n_views : g + 1, nv = v_end - v_begin;
     const int f0 = blockIdx.z * a.frames_per_cta, f1 = min(a.n_frames, f0 + a.frames_per_cta);
-    const bool sampler = warp < kSamplers / 32;              // warp 8 = TMA producer: no pixels of its own
-    const int lx = lane & 7, ly = 4 * (warp & 7) + (lane >> 3);  // pixel k of this thread: (lx + 8 k, ly)
+    const bool sampler = warp < kSamplers / 32;  // the last warp = TMA producer: no pixels of its own
+    const int sw = warp & (kSamplers / 32 - 1), band = sw / kWarpsPerBand, cg = sw % kWarpsPerBand;
+    // pixel k of this thread: column lx + 8 k, row ly
+    const int lx = 8 * kPx * cg + (lane & 7), ly = 4 * band + (lane >> 3);
     const int j = y0 + ly;
-    const bool full_tile = (x0 + kTile <= a.W) && (y0 + kTile <= a.H);
+    const bool full_tile = (x0 + kTileW <= a.W) && (y0 + M::kTileH <= a.H);
 
-    // ---- coordinates of this thread's 4 pixels ------------------------------------------------------------
+    // ---- coordinates of this thread's pixels --------------------------------------------------------------
     int sx[kPx], sy[kPx];
 #pragma unroll
     for (int k = 0; k < kPx; ++k) sx[k] = sy[k] = 0;
@@ -433,14 +495,14 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         mny = min(mny, s_red[w * 4 + 2]);
         mxy = max(mxy, s_red[w * 4 + 3]);
     }
-    const ViewArgs& v0 = a.view[v_begin];
-    const int bx0 = (3 * mnx) & ~15, bx1 = (3 * (mxx + 2) + 15) & ~15;  // byte range of the taps, 16-byte granules
-    const int wbytes = bx1 - bx0, nrows = mxy + 2 - mny;
+    // taps cover columns ix - kLo .. ix + kHi and rows iy - kLo .. iy + kHi
+    const int bx0 = (3 * (mnx - M::kLo)) & ~15, bx1 = (3 * (mxx + M::kHi + 1) + 15) & ~15;  // 16-byte granules
+    const int ry0 = mny - M::kLo;
+    const int wbytes = bx1 - bx0, nrows = mxy + M::kHi + 1 - ry0;
     // Taps outside the source read TMA's zero fill = BORDER_CONSTANT(0); only unbounded footprints (NaN / huge
     // coordinates saturate to +-32768) and partial edge tiles leave the fast path.
-    const bool fast = full_tile && wbytes <= kPitchWide && nrows <= kMaxRows && mnx > -32768 && mny > -32768 &&
-                      mxx < 32767 && mxy < 32767;
-    (void)v0;
+    const bool fast = full_tile && wbytes <= kPitchWide && nrows <= M::kRowsMin + (kRowSizes - 1) * kRowsStep &&
+                      mnx > -32768 && mny > -32768 && mxx < 32767 && mxy < 32767;
 
     if (!fast) {  // per-pixel gather from global memory with full border handling (rare tiles)
         if (sampler && j < a.H) {
@@ -454,7 +516,10 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                             const ViewArgs& vw = a.view[v];
                             Src s{vw.src + (long long)f * vw.frame_stride, vw.rows, vw.cols, vw.pitch};
                             int px[3];
-                            sample_linear<3>(s, sx[k], sy[k], VR180_BORDER_CONSTANT, a.bv, px);
+                            if (M::kInterp == VR180_INTER_LINEAR)
+                                sample_linear<3>(s, sx[k], sy[k], VR180_BORDER_CONSTANT, a.bv, px);
+                            else
+                                sample_tab<3, 4>(s, sx[k], sy[k], tp.tab, VR180_BORDER_CONSTANT, a.bv, px);
                             uint8_t* o = drow + (long long)(vw.dst_x_offset + i) * 3;
                             o[0] = (uint8_t)px[0];
                             o[1] = (uint8_t)px[1];
@@ -469,27 +534,27 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
 
     // ---- per-pixel constants of the frame loop ------------------------------------------------------------
     const int pitch = wbytes <= kPitchNarrow ? kPitchNarrow : kPitchWide;
-    PixelConst pc;
+    typename M::Pixel pc[kPx];
 #pragma unroll
     for (int k = 0; k < kPx; ++k) {
         const int ix = sx[k] >> kInterBits, iy = sy[k] >> kInterBits;
-        const int off = (iy - mny) * pitch + 3 * ix - bx0;
-        pc.boff[k] = off & ~3;
-        pc.sh[k] = (off & 3) * 8;
-        pack_weights(sx[k] & 31, sy[k] & 31, pc.W01[k], pc.W23[k]);
+        const int off = (iy - M::kLo - ry0) * pitch + 3 * (ix - M::kLo) - bx0;
+        pc[k].boff = off & ~3;
+        pc[k].sh = (off & 3) * 8;
+        if (sampler) M::weights(pc[k], sx[k] & 31, sy[k] & 31, tp.tab);
     }
     TileGeom tg;
     tg.nrows = nrows;
     tg.bx0 = bx0;
-    tg.mny = mny;
+    tg.ry0 = ry0;
     tg.x0 = x0;
     tg.y0 = y0;
     if (pitch == kPitchNarrow) {
-        if (nv == 2) frame_loop<2, kPitchNarrow>(a, tm, v_begin, f0, f1, pc, tg, smem);
-        else frame_loop<1, kPitchNarrow>(a, tm, v_begin, f0, f1, pc, tg, smem);
+        if (nv == 2) frame_loop<M, 2, kPitchNarrow>(a, tm, v_begin, f0, f1, pc, tg, smem, band, cg);
+        else frame_loop<M, 1, kPitchNarrow>(a, tm, v_begin, f0, f1, pc, tg, smem, band, cg);
     } else {
-        if (nv == 2) frame_loop<2, kPitchWide>(a, tm, v_begin, f0, f1, pc, tg, smem);
-        else frame_loop<1, kPitchWide>(a, tm, v_begin, f0, f1, pc, tg, smem);
+        if (nv == 2) frame_loop<M, 2, kPitchWide>(a, tm, v_begin, f0, f1, pc, tg, smem, band, cg);
+        else frame_loop<M, 1, kPitchWide>(a, tm, v_begin, f0, f1, pc, tg, smem, band, cg);
     }
 }
 
@@ -554,27 +619,11 @@ static bool encode_u8_3d(CUtensorMap* out, const void* base, long long row_bytes
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Host-side eligibility + launch.  Returns VR180_ERR_UNSUPPORTED when the request is outside the fast path (the
-// caller then launches the generic k_remap); any other value is final.
-int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr180_chain_t& c0, const vr180_chain_t& c1,
+template <class M>
+static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180_chain_t& c1, const short* tab,
                        cudaStream_t st) {
     using namespace tiled;
-    if (channels != 3 || interp != VR180_INTER_LINEAR || a0.border_mode != VR180_BORDER_CONSTANT) return VR180_ERR_UNSUPPORTED;
-    if (a0.bv[0] | a0.bv[1] | a0.bv[2]) return VR180_ERR_UNSUPPORTED;  // staged tiles assume a zero border colour
     const int n_groups = a0.share_map ? 1 : a0.n_views;
-    for (int v = 0; v < a0.n_views; ++v) {
-        const ViewArgs& vw = a0.view[v];
-        // TMA: 16-byte aligned base and strides
-        if (((uintptr_t)vw.src & 15) || (vw.pitch & 15) || (vw.frame_stride & 15) || vw.pitch < (long long)vw.cols * 3)
-            return VR180_ERR_UNSUPPORTED;
-        if (a0.n_frames > 1 && vw.frame_stride < vw.pitch * vw.rows) return VR180_ERR_UNSUPPORTED;
-        if (vw.rows != a0.view[0].rows || vw.cols != a0.view[0].cols) return VR180_ERR_UNSUPPORTED;
-    }
-    for (int g = 0; g < n_groups; ++g)
-        if (a0.view[g].map_kind == VR180_MAPSRC_ANALYTIC && a0.view[g].radius_dev) return VR180_ERR_UNSUPPORTED;
-    if (((uintptr_t)a0.dst & 15) || (a0.dst_pitch & 15) || (a0.dst_frame_stride & 15)) return VR180_ERR_UNSUPPORTED;
-    if (a0.n_frames > 1 && a0.dst_frame_stride < a0.dst_pitch * a0.H) return VR180_ERR_UNSUPPORTED;
-
     TmaMaps tm;
     memset(&tm, 0, sizeof(tm));
     for (int v = 0; v < a0.n_views; ++v) {
@@ -582,26 +631,28 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
         for (int w = 0; w < 2; ++w)
             for (int r = 0; r < kRowSizes; ++r)
                 if (!encode_u8_3d(&tm.src[v][w][r], vw.src, (long long)vw.cols * 3, vw.rows, a0.n_frames, vw.pitch,
-                                  vw.frame_stride, w ? kPitchWide : kPitchNarrow, kRowsMin + r * kRowsStep))
+                                  vw.frame_stride, w ? kPitchWide : kPitchNarrow, M::kRowsMin + r * kRowsStep))
                     return VR180_ERR_UNSUPPORTED;
     }
     if (a0.n_views == 1) memcpy(&tm.src[1], &tm.src[0], sizeof(tm.src[0]));
-    if (!encode_u8_3d(&tm.dst, a0.dst, a0.dst_pitch, a0.H, a0.n_frames, a0.dst_pitch, a0.dst_frame_stride, kTile * 3, kTile))
+    if (!encode_u8_3d(&tm.dst, a0.dst, a0.dst_pitch, a0.H, a0.n_frames, a0.dst_pitch, a0.dst_frame_stride, kTileW * 3,
+                      M::kTileH))
         return VR180_ERR_UNSUPPORTED;
 
     static std::atomic<int> attr_done[64];
     int dev = 0;
     VR180_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !attr_done[dev].load(std::memory_order_acquire)) {
-        VR180_CUDA(cudaFuncSetAttribute(k_warp_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        VR180_CUDA(cudaFuncSetAttribute(k_warp_tiled<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_done[dev].store(1, std::memory_order_release);
     }
 
     RemapArgs a = a0;
     TiledParams tp;
     memset(&tp, 0, sizeof(tp));
-    const int tiles_x = (a.W + kTile - 1) / kTile, tiles_y = (a.H + kTile - 1) / kTile;
+    const int tiles_x = (a.W + kTileW - 1) / kTileW, tiles_y = (a.H + M::kTileH - 1) / M::kTileH;
     tp.tiles_x = tiles_x;
+    tp.tab = tab;
     const long long tiles = (long long)tiles_x * tiles_y * n_groups;
     // frames per CTA: the coordinates are evaluated once per CTA, so keep the chunk as large as the grid allows
     int fpc = a.n_frames;
@@ -620,10 +671,36 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
         match_std_chain(c, tp.std[a.view[g].chain_idx ? 1 : 0]);
     }
     dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)n_groups, (unsigned)chunks);
-    k_warp_tiled<<<grid, kThreads, kSmemBytes, st>>>(a, c0, c1, tp, tm);
+    k_warp_tiled<M><<<grid, kThreads, kSmemBytes, st>>>(a, c0, c1, tp, tm);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     VR180_CUDA(cudaGetLastError());
     return VR180_OK;
+}
+
+// Host-side eligibility + launch.  Returns VR180_ERR_UNSUPPORTED when the request is outside the fast path (the
+// caller then launches the generic k_remap); any other value is final.  `tab_cubic`: device copy of the 1024 x 16
+// bicubic weight table.
+int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr180_chain_t& c0, const vr180_chain_t& c1,
+                       const short* tab_cubic, cudaStream_t st) {
+    if (channels != 3 || a0.border_mode != VR180_BORDER_CONSTANT) return VR180_ERR_UNSUPPORTED;
+    if (interp != VR180_INTER_LINEAR && interp != VR180_INTER_CUBIC) return VR180_ERR_UNSUPPORTED;
+    if (a0.bv[0] | a0.bv[1] | a0.bv[2]) return VR180_ERR_UNSUPPORTED;  // staged tiles assume a zero border colour
+    const int n_groups = a0.share_map ? 1 : a0.n_views;
+    for (int v = 0; v < a0.n_views; ++v) {
+        const ViewArgs& vw = a0.view[v];
+        // TMA: 16-byte aligned base and strides
+        if (((uintptr_t)vw.src & 15) || (vw.pitch & 15) || (vw.frame_stride & 15) || vw.pitch < (long long)vw.cols * 3)
+            return VR180_ERR_UNSUPPORTED;
+        if (a0.n_frames > 1 && vw.frame_stride < vw.pitch * vw.rows) return VR180_ERR_UNSUPPORTED;
+        if (vw.rows != a0.view[0].rows || vw.cols != a0.view[0].cols) return VR180_ERR_UNSUPPORTED;
+    }
+    for (int g = 0; g < n_groups; ++g)
+        if (a0.view[g].map_kind == VR180_MAPSRC_ANALYTIC && a0.view[g].radius_dev) return VR180_ERR_UNSUPPORTED;
+    if (((uintptr_t)a0.dst & 15) || (a0.dst_pitch & 15) || (a0.dst_frame_stride & 15)) return VR180_ERR_UNSUPPORTED;
+    if (a0.n_frames > 1 && a0.dst_frame_stride < a0.dst_pitch * a0.H) return VR180_ERR_UNSUPPORTED;
+    if (interp == VR180_INTER_LINEAR) return launch_mode<tiled::Linear>(a0, c0, c1, nullptr, st);
+    if (!tab_cubic) return VR180_ERR_UNSUPPORTED;
+    return launch_mode<tiled::Cubic>(a0, c0, c1, tab_cubic, st);
 }
 
 }  // namespace vr180
