@@ -43,7 +43,7 @@ POLY = [0, 1, -0.02, 0.003]
 
 WORKLOADS = {
     # name: (per-eye input n, output n, interpolation, per_eye_tuple, map_source, radius, default pairs per step)
-    "8k_rot_poly_linear": dict(n=4096, interp=1, tuple_=True, chain="rot_poly", src="analytic", radius="fixed", pairs=16,
+    "8k_rot_poly_linear": dict(n=4096, interp=1, tuple_=True, chain="rot_poly", src="analytic", radius="fixed", pairs=32,
                                desc="batched 8K stereo pairs (2x4096^2 -> 8192x4096), per-eye Euclidean3DRotator+"
                                     "PolynomialScaler, fused analytic warp, INTER_LINEAR [BASELINE configs[2], batched]"),
     "4k_pair_linear": dict(n=2048, interp=1, tuple_=False, chain="base", src="analytic", radius="fixed", pairs=1,
@@ -416,11 +416,13 @@ def run_gpu(args) -> dict:
     # total shards = world * pairs (weak scaling)
     value = main["value"] * world
     achieved = main["bytes_per_step"] / (main["ms_per_step"] / 1e3) / 1e9
-    traffic = None
+    traffic = None  # DRAM bytes (read + written) of one launch from the committed ncu capture of this workload
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get(args.workload)
+            t = json.loads(tp.read_text()).get(args.workload)
+            if t and int(t.get("pairs_per_launch", -1)) == int(main["pairs"]):
+                traffic = t["dram_bytes_per_launch"]
         except Exception:  # noqa: BLE001
             traffic = None
     line = {
@@ -432,9 +434,10 @@ def run_gpu(args) -> dict:
                    "parallelism": f"frames sharded over {world} GPU(s), no collective"},
         "gpu_launches": main["launches_per_step"] * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                     "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                      "algorithmic_bytes_per_launch": main["bytes_per_step"],
-                     "source_touched_fraction": main["touched_fraction"], "kernel": "k_remap (1 launch per step)"},
+                     "source_touched_fraction": main["touched_fraction"], "kernel": "vr180::tiled::k_warp_tiled (1 launch per step)"},
         "e2e": main.get("e2e"),
         "clocks": clocks,
     }

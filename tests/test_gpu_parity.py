@@ -342,6 +342,44 @@ def test_tiled_pipeline_ring_wraparound_and_source_edges(interp, per_eye):
         assert np.array_equal(got[f], want), (interp, per_eye, f, int((got[f] != want).sum()))
 
 
+@pytest.mark.parametrize("interp", [1, 2])
+@pytest.mark.parametrize("per_eye", [False, True])
+def test_tiled_per_frame_radius_on_device(interp, per_eye):
+    """Per-frame radius consumed on the device by the tiled kernel (vr180_mapsrc_t::radius_dev): every frame has
+    its own source rectangle.  Radii: small, larger than the source (edges), negative / x.5 (what get_radius
+    really returns) and NaN (no transition found -> all border)."""
+    import torch
+
+    hin, win, wout, hout = 192, 224, 160, 96
+    radii = [90.0, 150.0, float("nan"), -100.5, 60.25, 111.0, 149.5, -75.0, 33.0, 128.0, 95.5]
+    n = len(radii)
+    ql, qr = V.from_rotation_vector([0.03, -0.02, 0.05]), V.from_rotation_vector([-0.03, 0.02, -0.05])
+    mk = lambda q: (V.EquirectangularEncoder() * V.Euclidean3DRotator(q) * V.PolynomialScaler([0, 1, 0.05])  # noqa: E731
+                    * V.FisheyeDecoder("equidistant"))
+    t = (mk(ql), mk(qr)) if per_eye else mk(ql)
+    rng = np.random.default_rng(11)
+    ln = rng.integers(0, 256, (n, hin, win, 3), dtype=np.uint8)
+    rn = rng.integers(0, 256, (n, hin, win, 3), dtype=np.uint8)
+    left, right = torch.from_numpy(ln).cuda(), torch.from_numpy(rn).cuda()
+    wp = V.SbsWarper(t, size_input=(hin, win), size_output=(wout, hout), interpolation=interp, radius="auto")
+    got = wp(left, right, radius=torch.tensor(radii, dtype=torch.float64, device="cuda")).cpu().numpy()
+
+    def omap(q, r):
+        ops = [("equirect_enc", True), ("rot3", chain_np.quat_to_matrix(*q.components).ravel().tolist()),
+               ("poly", [0, 1, 0.05]), ("fisheye_dec", "equidistant")]
+        return chain_np.get_map(ops, radius=r, size_input=(hin, win), size_output=(wout, hout))
+
+    for f, r in enumerate(radii):
+        if r != r:
+            assert not got[f].any(), f  # NaN coordinates sample the (zero) border colour everywhere
+            continue
+        ml = omap(ql, r)
+        mr = omap(qr, r) if per_eye else ml
+        want = np.concatenate([cv2.remap(ln[f], ml[0], ml[1], interpolation=interp),
+                               cv2.remap(rn[f], mr[0], mr[1], interpolation=interp)], axis=1)
+        assert np.array_equal(got[f], want), (interp, per_eye, f, r, int((got[f] != want).sum()))
+
+
 # ---------------------------------------------------------------------------------------------------------
 # (6) full BASELINE sizes through size-independent properties
 # ---------------------------------------------------------------------------------------------------------

@@ -59,7 +59,9 @@ constexpr int kOffOut = kStageArea;
 constexpr int kOffTrig = kOffOut + kOutArea;
 constexpr int kOffRed = kOffTrig + 4 * 32 * 8;
 constexpr int kOffBar = kOffRed + 8 * 4 * 4;  // full[kMaxStages], empty[kMaxStages], ofull[kOutBufs], oempty[kOutBufs]
-constexpr int kSmemBytes = kOffBar + (2 * kMaxStages + 2 * kOutBufs) * 8;
+constexpr int kOffOrg = kOffBar + (2 * kMaxStages + 2 * kOutBufs) * 8;  // int2 origin of the rectangle in each stage
+constexpr int kOffExt = kOffOrg + kMaxStages * 8;                         // double[8][4] per-warp normalised extremes
+constexpr int kSmemBytes = kOffExt + 8 * 4 * 8;
 
 // The standard chain shape, lowered once on the host (see match_std_chain):
 //   Normalize, EquirectangularEncoder, [Euclidean3DRotator], [PolynomialScaler], FisheyeDecoder("equidistant"),
@@ -219,6 +221,25 @@ struct Cubic {
     }
 };
 
+// Per-frame radius (vr180_mapsrc_t::radius_dev): the chain is evaluated WITHOUT its final DenormalizeTransformer
+// once per tile; frame f then only applies  x = nx * radius[f] + cx  (transformer.py:202-203), rounds to float32
+// and quantises.  That composition is monotone in nx, so the integer bounding box of a tile in frame f follows
+// from the tile's extreme normalised coordinates.
+struct DynRadius {
+    const double* radius;  // device, one per frame; nullptr = radius baked into the chain
+    double cx, cy;         // centre of the final DenormalizeTransformer
+    double ext[4];         // tile extremes: nx min, nx max, ny min, ny max
+};
+__device__ __forceinline__ int denorm_q(double n, double rad, double c) {  // astype(float32), cvRound(x * 32)
+    return quantise(__double2float_rn(add_rn(mul_rn(n, rad), c)));
+}
+// integer pixel range [lo, hi] of the taps' base coordinate over the tile for one frame
+__device__ __forceinline__ void dyn_range(double nmin, double nmax, double rad, double c, int& lo, int& hi) {
+    const int a = sat16(denorm_q(nmin, rad, c) >> kInterBits), b = sat16(denorm_q(nmax, rad, c) >> kInterBits);
+    lo = min(a, b);
+    hi = max(a, b);
+}
+
 struct TileGeom {
     int nrows;          // source rows of the tile's rectangle
     int bx0, ry0;       // first source byte column (16-aligned, may be negative) and first source row
@@ -243,15 +264,17 @@ struct TileGeom {
 //                              (4 deep); the producer waits, then issues the TMA store
 //   oempty[o]  (1)             the producer arrives when the store that last used out buffer o has finished reading
 //                              it (bulk wait_group.read); the sampling warps wait before rewriting it (item n - 4)
-template <class M, int NV, int PITCH>
+template <class M, int NV, int PITCH, bool DYN>
 __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm, int v_begin, int f0, int f1,
                                            const typename M::Pixel (&pc)[M::kPx], const TileGeom& tg, uint8_t* smem,
-                                           int band, int cg) {
+                                           int band, int cg, const DynRadius& dr, const double (&nx)[M::kPx],
+                                           const double (&ny)[M::kPx], const short* tab) {
     constexpr int kOutTileBytes = M::kTileH * kTileW * 3;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s_stage = smem_u32(smem), s_full = s_stage + kOffBar, s_empty = s_full + kMaxStages * 8;
     const uint32_t s_ofull = s_empty + kMaxStages * 8, s_oempty = s_ofull + kOutBufs * 8, s_out = s_stage + kOffOut;
 
+    int2* const s_org = reinterpret_cast<int2*>(smem + kOffOrg);
     const int n_items = (f1 - f0) * NV;
     const int rsel = tg.nrows <= M::kRowsMin ? 0 : (tg.nrows - M::kRowsMin + kRowsStep - 1) / kRowsStep;
     const int stage_bytes = (M::kRowsMin + rsel * kRowsStep) * PITCH;  // multiple of 128
@@ -267,8 +290,22 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
             const uint32_t bar = s_full + p_stage * 8;
             const int v = (NV == 2) ? (p_item & 1) : 0, f = f0 + ((NV == 2) ? (p_item >> 1) : p_item);
             if (p_use > 0) mbar_wait(s_empty + p_stage * 8, (uint32_t)(p_use + 1) & 1u);
+            int bx0 = tg.bx0, ry0 = tg.ry0;
+            if (DYN) {  // this frame's rectangle; its origin travels to the samplers next to the stage
+                const double rad = __ldg(dr.radius + f);
+                if (rad == rad) {
+                    int lo, hi;
+                    dyn_range(dr.ext[0], dr.ext[1], rad, dr.cx, lo, hi);
+                    bx0 = (3 * (lo - M::kLo)) & ~15;
+                    dyn_range(dr.ext[2], dr.ext[3], rad, dr.cy, lo, hi);
+                    ry0 = lo - M::kLo;
+                } else {  // get_radius found no transition: every coordinate is NaN -> border colour
+                    bx0 = ry0 = -(1 << 20);
+                }
+                s_org[p_stage] = make_int2(bx0, ry0);  // released to the samplers by the arrive below
+            }
             mbar_expect_tx(bar, (uint32_t)stage_bytes);
-            tma_load_3d(s_stage + p_stage * stage_bytes, map0 + v * (2 * kRowSizes), tg.bx0, tg.ry0, f, bar);
+            tma_load_3d(s_stage + p_stage * stage_bytes, map0 + v * (2 * kRowSizes), bx0, ry0, f, bar);
             ++p_item;
             if (++p_stage == S) { p_stage = 0; ++p_use; }
         };
@@ -304,8 +341,25 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
         mbar_wait(s_full + st * 8, ph);
         const uint8_t* buf = smem + st * stage_bytes;
         uint32_t res[M::kPx];
+        if (DYN) {
+            const int f = f0 + ((NV == 2) ? (n >> 1) : n);
+            const double rad = __ldg(dr.radius + f);
+            const int2 org = s_org[st];
+            const bool have = rad == rad;
 #pragma unroll
-        for (int k = 0; k < M::kPx; ++k) res[k] = M::template sample<PITCH>(buf, pc[k]);
+            for (int k = 0; k < M::kPx; ++k) {
+                typename M::Pixel px;
+                const int qx = denorm_q(nx[k], rad, dr.cx), qy = denorm_q(ny[k], rad, dr.cy);
+                const int off = ((qy >> kInterBits) - M::kLo - org.y) * PITCH + 3 * ((qx >> kInterBits) - M::kLo) - org.x;
+                px.boff = have ? (off & ~3) : 0;
+                px.sh = (off & 3) * 8;
+                M::weights(px, qx & 31, qy & 31, tab);
+                res[k] = have ? M::template sample<PITCH>(buf, px) : 0u;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < M::kPx; ++k) res[k] = M::template sample<PITCH>(buf, pc[k]);
+        }
         uint32_t word[M::kPx];
 #pragma unroll
         for (int k = 0; k < M::kPx; ++k) {
@@ -329,7 +383,7 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     }
 }
 
-template <class M>
+template <class M, bool DYN>  // DYN: per-frame radius from device memory (vr180_mapsrc_t::radius_dev)
 __global__ void __launch_bounds__(kThreads, 4)
 k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_chain_t chain0,
              const __grid_constant__ vr180_chain_t chain1, const __grid_constant__ TiledParams tp,
@@ -368,8 +422,13 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
 
     // ---- coordinates of this thread's pixels --------------------------------------------------------------
     int sx[kPx], sy[kPx];
+    double nx[kPx], ny[kPx];  // dyn: coordinates before the final Denormalize
 #pragma unroll
-    for (int k = 0; k < kPx; ++k) sx[k] = sy[k] = 0;
+    for (int k = 0; k < kPx; ++k) {
+        sx[k] = sy[k] = 0;
+        nx[k] = ny[k] = 0.0;
+    }
+    constexpr bool dyn = DYN;  // host guarantees: DYN <=> every map group is ANALYTIC with a radius_dev
     if (mv.map_kind == VR180_MAPSRC_ANALYTIC) {
         const vr180_chain_t& ch = mv.chain_idx ? chain1 : chain0;
         const StdChain& sc = tp.std[mv.chain_idx ? 1 : 0];
@@ -416,9 +475,15 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                         if (c.has_rot) op_rot3(c.R, s);
                         if (c.n_poly >= 0) op_poly(c.poly, c.n_poly, s);
                         op_fisheye_dec(VR180_MAP_EQUIDISTANT, s);
-                        op_denormalize(c.den, s);
-                        sx[k] = quantise(__double2float_rn(s.x));  // astype(float32) then cvRound(x * 32)
-                        sy[k] = quantise(__double2float_rn(s.y));
+                        if (dyn) {
+                            to_xy(s);
+                            nx[k] = s.x;
+                            ny[k] = s.y;
+                        } else {
+                            op_denormalize(c.den, s);
+                            sx[k] = quantise(__double2float_rn(s.x));  // astype(float32) then cvRound(x * 32)
+                            sy[k] = quantise(__double2float_rn(s.y));
+                        }
                     }
                 };
                 if (mv.chain_idx) std_eval(tp.std[1]);
@@ -428,23 +493,24 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                 for (int k = 0; k < kPx; ++k) {
                     ChainState s;
                     seed(k, s);
-                    run_ops(ch, 2, ch.n_ops, s);
+                    run_ops(ch, 2, ch.n_ops - (dyn ? 1 : 0), s);
                     to_xy(s);
                     const int qx = quantise(__double2float_rn(s.x)), qy = quantise(__double2float_rn(s.y));
 #pragma unroll
                     for (int kk = 0; kk < kPx; ++kk)
-                        if (kk == k) { sx[kk] = qx; sy[kk] = qy; }
+                        if (kk == k) { sx[kk] = qx; sy[kk] = qy; nx[kk] = s.x; ny[kk] = s.y; }
                 }
             }
         } else if (sampler) {
 #pragma unroll 1
             for (int k = 0; k < kPx; ++k) {
                 double xs, ys;
-                eval_chain(ch, x0 + lx + 8 * k, j, xs, ys);
+                if (dyn) eval_chain_normalised(ch, x0 + lx + 8 * k, j, xs, ys);
+                else eval_chain(ch, x0 + lx + 8 * k, j, xs, ys);
                 const int qx = quantise(__double2float_rn(xs)), qy = quantise(__double2float_rn(ys));
 #pragma unroll
                 for (int kk = 0; kk < kPx; ++kk)
-                    if (kk == k) { sx[kk] = qx; sy[kk] = qy; }
+                    if (kk == k) { sx[kk] = qx; sy[kk] = qy; nx[kk] = xs; ny[kk] = ys; }
             }
         }
     } else if (sampler) {
@@ -485,7 +551,39 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         s_red[warp * 4 + 2] = mny;
         s_red[warp * 4 + 3] = mxy;
     }
-    __syncthreads();
+    DynRadius dr;
+    dr.radius = nullptr;
+    dr.cx = dr.cy = 0.0;
+    dr.ext[0] = dr.ext[1] = dr.ext[2] = dr.ext[3] = 0.0;
+    int nan_px = 0;
+    if (dyn) {  // tile extremes of the normalised coordinates (frame independent)
+        double* s_ext = reinterpret_cast<double*>(smem + kOffExt);
+        double e0 = CUDART_INF, e1 = -CUDART_INF, e2 = CUDART_INF, e3 = -CUDART_INF;
+        if (sampler) {
+#pragma unroll
+            for (int k = 0; k < kPx; ++k) {
+                nan_px |= (nx[k] != nx[k]) | (ny[k] != ny[k]);
+                e0 = fmin(e0, nx[k]);
+                e1 = fmax(e1, nx[k]);
+                e2 = fmin(e2, ny[k]);
+                e3 = fmax(e3, ny[k]);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            e0 = fmin(e0, __shfl_xor_sync(0xffffffffu, e0, d));
+            e1 = fmax(e1, __shfl_xor_sync(0xffffffffu, e1, d));
+            e2 = fmin(e2, __shfl_xor_sync(0xffffffffu, e2, d));
+            e3 = fmax(e3, __shfl_xor_sync(0xffffffffu, e3, d));
+        }
+        if (lane == 0 && sampler) {
+            s_ext[warp * 4 + 0] = e0;
+            s_ext[warp * 4 + 1] = e1;
+            s_ext[warp * 4 + 2] = e2;
+            s_ext[warp * 4 + 3] = e3;
+        }
+    }
+    nan_px = __syncthreads_or(nan_px);
     mnx = mny = INT_MAX;
     mxx = mxy = INT_MIN;
 #pragma unroll
@@ -501,8 +599,44 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     const int wbytes = bx1 - bx0, nrows = mxy + M::kHi + 1 - ry0;
     // Taps outside the source read TMA's zero fill = BORDER_CONSTANT(0); only unbounded footprints (NaN / huge
     // coordinates saturate to +-32768) and partial edge tiles leave the fast path.
-    const bool fast = full_tile && wbytes <= kPitchWide && nrows <= M::kRowsMin + (kRowSizes - 1) * kRowsStep &&
-                      mnx > -32768 && mny > -32768 && mxx < 32767 && mxy < 32767;
+    bool fast = full_tile && wbytes <= kPitchWide && nrows <= M::kRowsMin + (kRowSizes - 1) * kRowsStep &&
+                mnx > -32768 && mny > -32768 && mxx < 32767 && mxy < 32767;
+    int dyn_wbytes = 0, dyn_nrows = 0;
+    if (dyn) {
+        const double* s_ext = reinterpret_cast<const double*>(smem + kOffExt);
+        dr.ext[0] = dr.ext[2] = CUDART_INF;
+        dr.ext[1] = dr.ext[3] = -CUDART_INF;
+#pragma unroll
+        for (int w = 0; w < kSamplers / 32; ++w) {
+            dr.ext[0] = fmin(dr.ext[0], s_ext[w * 4 + 0]);
+            dr.ext[1] = fmax(dr.ext[1], s_ext[w * 4 + 1]);
+            dr.ext[2] = fmin(dr.ext[2], s_ext[w * 4 + 2]);
+            dr.ext[3] = fmax(dr.ext[3], s_ext[w * 4 + 3]);
+        }
+        const vr180_chain_t& ch = mv.chain_idx ? chain1 : chain0;
+        dr.radius = mv.radius_dev;
+        dr.cx = ch.ops[ch.n_ops - 1].p[2];
+        dr.cy = ch.ops[ch.n_ops - 1].p[3];
+        // largest rectangle over the frames of this chunk (lanes stride over the frames; every warp redundantly)
+        int ok = 1;
+        for (int f = f0 + lane; f < f1; f += 32) {
+            const double rad = __ldg(dr.radius + f);
+            if (rad == rad) {
+                int lo, hi;
+                dyn_range(dr.ext[0], dr.ext[1], rad, dr.cx, lo, hi);
+                ok &= (lo > -32768) & (hi < 32767);
+                dyn_wbytes = max(dyn_wbytes, ((3 * (hi + M::kHi + 1) + 15) & ~15) - ((3 * (lo - M::kLo)) & ~15));
+                dyn_range(dr.ext[2], dr.ext[3], rad, dr.cy, lo, hi);
+                ok &= (lo > -32768) & (hi < 32767);
+                dyn_nrows = max(dyn_nrows, hi + M::kHi + 1 - (lo - M::kLo));
+            }
+        }
+        dyn_wbytes = __reduce_max_sync(0xffffffffu, dyn_wbytes);
+        dyn_nrows = __reduce_max_sync(0xffffffffu, dyn_nrows);
+        ok = __all_sync(0xffffffffu, ok);
+        fast = full_tile && ok && !nan_px && dyn_wbytes <= kPitchWide &&
+               dyn_nrows <= M::kRowsMin + (kRowSizes - 1) * kRowsStep;
+    }
 
     if (!fast) {  // per-pixel gather from global memory with full border handling (rare tiles)
         if (sampler && j < a.H) {
@@ -512,14 +646,20 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                 if (i < a.W) {
                     for (int f = f0; f < f1; ++f) {
                         uint8_t* drow = a.dst + (long long)f * a.dst_frame_stride + (long long)j * a.dst_pitch;
+                        int qx = sx[k], qy = sy[k];
+                        if (dyn) {
+                            const double rad = __ldg(dr.radius + f);
+                            qx = denorm_q(nx[k], rad, dr.cx);
+                            qy = denorm_q(ny[k], rad, dr.cy);
+                        }
                         for (int v = v_begin; v < v_end; ++v) {
                             const ViewArgs& vw = a.view[v];
                             Src s{vw.src + (long long)f * vw.frame_stride, vw.rows, vw.cols, vw.pitch};
                             int px[3];
                             if (M::kInterp == VR180_INTER_LINEAR)
-                                sample_linear<3>(s, sx[k], sy[k], VR180_BORDER_CONSTANT, a.bv, px);
+                                sample_linear<3>(s, qx, qy, VR180_BORDER_CONSTANT, a.bv, px);
                             else
-                                sample_tab<3, 4>(s, sx[k], sy[k], tp.tab, VR180_BORDER_CONSTANT, a.bv, px);
+                                sample_tab<3, 4>(s, qx, qy, tp.tab, VR180_BORDER_CONSTANT, a.bv, px);
                             uint8_t* o = drow + (long long)(vw.dst_x_offset + i) * 3;
                             o[0] = (uint8_t)px[0];
                             o[1] = (uint8_t)px[1];
@@ -533,7 +673,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     }
 
     // ---- per-pixel constants of the frame loop ------------------------------------------------------------
-    const int pitch = wbytes <= kPitchNarrow ? kPitchNarrow : kPitchWide;
+    const int pitch = (dyn ? dyn_wbytes : wbytes) <= kPitchNarrow ? kPitchNarrow : kPitchWide;
     typename M::Pixel pc[kPx];
 #pragma unroll
     for (int k = 0; k < kPx; ++k) {
@@ -541,21 +681,19 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         const int off = (iy - M::kLo - ry0) * pitch + 3 * (ix - M::kLo) - bx0;
         pc[k].boff = off & ~3;
         pc[k].sh = (off & 3) * 8;
-        if (sampler) M::weights(pc[k], sx[k] & 31, sy[k] & 31, tp.tab);
+        if (sampler && !dyn) M::weights(pc[k], sx[k] & 31, sy[k] & 31, tp.tab);
     }
     TileGeom tg;
-    tg.nrows = nrows;
+    tg.nrows = dyn ? dyn_nrows : nrows;
     tg.bx0 = bx0;
     tg.ry0 = ry0;
     tg.x0 = x0;
     tg.y0 = y0;
-    if (pitch == kPitchNarrow) {
-        if (nv == 2) frame_loop<M, 2, kPitchNarrow>(a, tm, v_begin, f0, f1, pc, tg, smem, band, cg);
-        else frame_loop<M, 1, kPitchNarrow>(a, tm, v_begin, f0, f1, pc, tg, smem, band, cg);
-    } else {
-        if (nv == 2) frame_loop<M, 2, kPitchWide>(a, tm, v_begin, f0, f1, pc, tg, smem, band, cg);
-        else frame_loop<M, 1, kPitchWide>(a, tm, v_begin, f0, f1, pc, tg, smem, band, cg);
-    }
+#define VR180_LOOP(NV_, PITCH_, DYN_) \
+    frame_loop<M, NV_, PITCH_, DYN_>(a, tm, v_begin, f0, f1, pc, tg, smem, band, cg, dr, nx, ny, tp.tab)
+    if (pitch == kPitchNarrow) { if (nv == 2) VR180_LOOP(2, kPitchNarrow, DYN); else VR180_LOOP(1, kPitchNarrow, DYN); }
+    else                       { if (nv == 2) VR180_LOOP(2, kPitchWide, DYN);   else VR180_LOOP(1, kPitchWide, DYN); }
+#undef VR180_LOOP
 }
 
 }  // namespace tiled
@@ -619,7 +757,7 @@ static bool encode_u8_3d(CUtensorMap* out, const void* base, long long row_bytes
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <class M>
+template <class M, bool DYN>
 static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180_chain_t& c1, const short* tab,
                        cudaStream_t st) {
     using namespace tiled;
@@ -643,7 +781,7 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
     int dev = 0;
     VR180_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !attr_done[dev].load(std::memory_order_acquire)) {
-        VR180_CUDA(cudaFuncSetAttribute(k_warp_tiled<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        VR180_CUDA(cudaFuncSetAttribute(k_warp_tiled<M, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_done[dev].store(1, std::memory_order_release);
     }
 
@@ -671,7 +809,7 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
         match_std_chain(c, tp.std[a.view[g].chain_idx ? 1 : 0]);
     }
     dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)n_groups, (unsigned)chunks);
-    k_warp_tiled<M><<<grid, kThreads, kSmemBytes, st>>>(a, c0, c1, tp, tm);
+    k_warp_tiled<M, DYN><<<grid, kThreads, kSmemBytes, st>>>(a, c0, c1, tp, tm);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     VR180_CUDA(cudaGetLastError());
     return VR180_OK;
@@ -694,13 +832,20 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
         if (a0.n_frames > 1 && vw.frame_stride < vw.pitch * vw.rows) return VR180_ERR_UNSUPPORTED;
         if (vw.rows != a0.view[0].rows || vw.cols != a0.view[0].cols) return VR180_ERR_UNSUPPORTED;
     }
-    for (int g = 0; g < n_groups; ++g)
-        if (a0.view[g].map_kind == VR180_MAPSRC_ANALYTIC && a0.view[g].radius_dev) return VR180_ERR_UNSUPPORTED;
     if (((uintptr_t)a0.dst & 15) || (a0.dst_pitch & 15) || (a0.dst_frame_stride & 15)) return VR180_ERR_UNSUPPORTED;
     if (a0.n_frames > 1 && a0.dst_frame_stride < a0.dst_pitch * a0.H) return VR180_ERR_UNSUPPORTED;
-    if (interp == VR180_INTER_LINEAR) return launch_mode<tiled::Linear>(a0, c0, c1, nullptr, st);
+    // per-frame radius: all map groups or none (a mixed request takes the generic kernel)
+    int n_dyn = 0;
+    for (int g = 0; g < n_groups; ++g)
+        n_dyn += (a0.view[g].map_kind == VR180_MAPSRC_ANALYTIC && a0.view[g].radius_dev) ? 1 : 0;
+    if (n_dyn != 0 && n_dyn != n_groups) return VR180_ERR_UNSUPPORTED;
+    const bool dyn = n_dyn != 0;
+    if (interp == VR180_INTER_LINEAR)
+        return dyn ? launch_mode<tiled::Linear, true>(a0, c0, c1, nullptr, st)
+                   : launch_mode<tiled::Linear, false>(a0, c0, c1, nullptr, st);
     if (!tab_cubic) return VR180_ERR_UNSUPPORTED;
-    return launch_mode<tiled::Cubic>(a0, c0, c1, tab_cubic, st);
+    return dyn ? launch_mode<tiled::Cubic, true>(a0, c0, c1, tab_cubic, st)
+               : launch_mode<tiled::Cubic, false>(a0, c0, c1, tab_cubic, st);
 }
 
 }  // namespace vr180

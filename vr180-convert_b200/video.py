@@ -132,8 +132,11 @@ class SbsWarper:
                                          self._radius_buf.data_ptr(), stream), "vr180_get_radius")
         return self._radius_buf[:n], self._trans_buf[:n]
 
-    def __call__(self, left, right, out=None):
-        """left / right: uint8 CUDA tensors (F, rows, cols, C) -> out (F, H, 2W, C), eyes side by side."""
+    def __call__(self, left, right, out=None, radius=None):
+        """left / right: uint8 CUDA tensors (F, rows, cols, C) -> out (F, H, 2W, C), eyes side by side.
+
+        `radius` (plans built with radius="auto" only): float64 CUDA tensor (F,) of per-frame radii to use instead
+        of running get_radius, e.g. radii estimated once and smoothed over a clip; NaN = "no transition found"."""
         torch = self.torch
         n = left.shape[0]
         if right.shape != left.shape:
@@ -149,7 +152,13 @@ class SbsWarper:
             p.border_value[i] = b
         p.dst, p.dst_pitch, p.dst_frame_stride = out.data_ptr(), out.stride(1), out.stride(0)
         radius_dev = None
-        if self.auto_radius:
+        if radius is not None:
+            if not self.auto_radius:
+                raise ValueError('per-frame radii need a plan built with radius="auto"')
+            if radius.dtype != torch.float64 or radius.dim() != 1 or radius.shape[0] != n or not radius.is_contiguous():
+                raise ValueError(f"radius must be a contiguous float64 CUDA tensor of shape ({n},)")
+            radius_dev = radius
+        elif self.auto_radius:
             radius_dev, _ = self.radius_per_frame(left, right)
         for v, frames in enumerate((left, right)):
             vw = p.view[v]
