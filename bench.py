@@ -438,7 +438,10 @@ def run_gpu(args) -> dict:
                      "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                      "algorithmic_bytes_per_launch": main["bytes_per_step"],
                      "source_touched_fraction": main["touched_fraction"], "kernel": "vr180::tiled::k_warp_tiled (1 launch per step)"},
-        "e2e": main.get("e2e"),
+        "e2e": ({**main["e2e"], "value": main["e2e"]["value"] * world, "per_gpu_value": main["e2e"]["value"],
+                 "h2d_bytes_per_step": main["e2e"]["h2d_bytes_per_step"] * world,
+                 "d2h_bytes_per_step": main["e2e"]["d2h_bytes_per_step"] * world}
+                if main.get("e2e") else None),
         "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

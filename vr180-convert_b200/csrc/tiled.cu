@@ -255,13 +255,12 @@ struct TileGeom {
 // TMA-issue bound (~50 clk per operation, profiles/r1_v7_*).
 //
 // The staging area is a ring of S stages of exactly the tile's footprint (box rows x PITCH bytes), so a typical
-// bilinear tile (40 rows x 160 B = 6.4 KB) gets S = 6 and the loads run D = S - 2 items ahead of the sampling.
-// No CTA-wide barrier; four kinds of mbarrier:
+// bilinear tile (40 rows x 160 B = 6.4 KB) gets S = 6 and the loads run up to S - 1 items ahead of the sampling.
+// No CTA-wide barrier; three kinds of mbarrier:
 //   full[s]    (1 + tx bytes)  the box of the item in stage s has landed; the sampling warps wait on it
-//   empty[s]   (8)             one arrive per sampling warp when it is done reading stage s; the producer waits
-//                              before re-filling (with D = S - 2 that is the stage of item n - 2)
 //   ofull[o]   (8)             one arrive per sampling warp when its rows of the output tile are in out buffer o
-//                              (4 deep); the producer waits, then issues the TMA store
+//                              (4 deep) -- which also says the warp has left the item's stage; the producer waits,
+//                              issues the TMA store of the tile and re-fills the stage with item n + S
 //   oempty[o]  (1)             the producer arrives when the store that last used out buffer o has finished reading
 //                              it (bulk wait_group.read); the sampling warps wait before rewriting it (item n - 4)
 template <class M, int NV, int PITCH, bool DYN>
@@ -271,25 +270,24 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
                                            const double (&ny)[M::kPx], const short* tab) {
     constexpr int kOutTileBytes = M::kTileH * kTileW * 3;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t s_stage = smem_u32(smem), s_full = s_stage + kOffBar, s_empty = s_full + kMaxStages * 8;
-    const uint32_t s_ofull = s_empty + kMaxStages * 8, s_oempty = s_ofull + kOutBufs * 8, s_out = s_stage + kOffOut;
+    const uint32_t s_stage = smem_u32(smem), s_full = s_stage + kOffBar;
+    const uint32_t s_ofull = s_full + 2 * kMaxStages * 8, s_oempty = s_ofull + kOutBufs * 8, s_out = s_stage + kOffOut;
 
     int2* const s_org = reinterpret_cast<int2*>(smem + kOffOrg);
     const int n_items = (f1 - f0) * NV;
     const int rsel = tg.nrows <= M::kRowsMin ? 0 : (tg.nrows - M::kRowsMin + kRowsStep - 1) / kRowsStep;
     const int stage_bytes = (M::kRowsMin + rsel * kRowsStep) * PITCH;  // multiple of 128
-    const int S = min(kMaxStages, kStageArea / stage_bytes), D = S <= 3 ? S - 1 : S - 2;
+    const int S = min(kMaxStages, kStageArea / stage_bytes);
 
     if (warp == kSamplers / 32) {  // ---- producer ----
         if (lane != 0) return;
         const CUtensorMap* const map0 = &tm.src[v_begin][PITCH == kPitchWide ? 1 : 0][rsel];
         const int dst_x0 = (a.view[v_begin].dst_x_offset + tg.x0) * 3;
         const int dst_x1 = (a.view[v_begin + NV - 1].dst_x_offset + tg.x0) * 3;
-        int p_item = 0, p_stage = 0, p_use = 0;  // next item to fetch, its stage, how often that stage was filled
+        int p_item = 0, p_stage = 0;  // next item to fetch and its stage
         auto load = [&]() {
             const uint32_t bar = s_full + p_stage * 8;
             const int v = (NV == 2) ? (p_item & 1) : 0, f = f0 + ((NV == 2) ? (p_item >> 1) : p_item);
-            if (p_use > 0) mbar_wait(s_empty + p_stage * 8, (uint32_t)(p_use + 1) & 1u);
             int bx0 = tg.bx0, ry0 = tg.ry0;
             if (DYN) {  // this frame's rectangle; its origin travels to the samplers next to the stage
                 const double rad = __ldg(dr.radius + f);
@@ -307,16 +305,16 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
             mbar_expect_tx(bar, (uint32_t)stage_bytes);
             tma_load_3d(s_stage + p_stage * stage_bytes, map0 + v * (2 * kRowSizes), bx0, ry0, f, bar);
             ++p_item;
-            if (++p_stage == S) { p_stage = 0; ++p_use; }
+            if (++p_stage == S) p_stage = 0;
         };
-        for (int n = 0; n < D && n < n_items; ++n) load();
+        for (int n = 0; n < S && n < n_items; ++n) load();  // fill the ring
         for (int n = 0; n < n_items; ++n) {
-            if (n + D < n_items) load();
             const int o = n & (kOutBufs - 1);
             const int v = (NV == 2) ? (n & 1) : 0, f = f0 + ((NV == 2) ? (n >> 1) : n);
             mbar_wait(s_ofull + o * 8, (uint32_t)(n / kOutBufs) & 1u);  // every sampling warp has written item n
             tma_store_3d(&tm.dst, v ? dst_x1 : dst_x0, tg.y0, f, s_out + o * kOutTileBytes);
             bulk_commit();
+            if (n + S < n_items) load();  // ofull(n) also means: every warp has left the stage of item n -> re-fill it
             if (n >= 1) {
                 bulk_wait_read<1>();  // the store of item n - 1 has finished reading its out buffer
                 mbar_arrive(s_oempty + ((n - 1) & (kOutBufs - 1)) * 8);
@@ -375,10 +373,7 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(s_ofull + o * 8);   // this warp's rows of item n are in out[o]
-            mbar_arrive(s_empty + st * 8);  // this warp is done with stage st
-        }
+        if (lane == 0) mbar_arrive(s_ofull + o * 8);  // this warp's rows of item n are in out[o]; it has left stage st
         if (++st == S) { st = 0; ph ^= 1u; }
     }
 }
@@ -762,20 +757,54 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
                        cudaStream_t st) {
     using namespace tiled;
     const int n_groups = a0.share_map ? 1 : a0.n_views;
-    TmaMaps tm;
-    memset(&tm, 0, sizeof(tm));
+    // The descriptors depend only on the buffers' geometry: video loops call with the same buffers again and again,
+    // so the last set is kept per host thread (21 cuTensorMapEncodeTiled calls cost ~20 us).
+    struct Key {
+        const void* src[2];
+        long long pitch[2], fs[2];
+        int rows, cols, n_views, n_frames, H, mode;
+        const void* dst;
+        long long dst_pitch, dst_fs;
+    };
+    Key key;
+    memset(&key, 0, sizeof(key));
     for (int v = 0; v < a0.n_views; ++v) {
-        const ViewArgs& vw = a0.view[v];
-        for (int w = 0; w < 2; ++w)
-            for (int r = 0; r < kRowSizes; ++r)
-                if (!encode_u8_3d(&tm.src[v][w][r], vw.src, (long long)vw.cols * 3, vw.rows, a0.n_frames, vw.pitch,
-                                  vw.frame_stride, w ? kPitchWide : kPitchNarrow, M::kRowsMin + r * kRowsStep))
-                    return VR180_ERR_UNSUPPORTED;
+        key.src[v] = a0.view[v].src;
+        key.pitch[v] = a0.view[v].pitch;
+        key.fs[v] = a0.view[v].frame_stride;
     }
-    if (a0.n_views == 1) memcpy(&tm.src[1], &tm.src[0], sizeof(tm.src[0]));
-    if (!encode_u8_3d(&tm.dst, a0.dst, a0.dst_pitch, a0.H, a0.n_frames, a0.dst_pitch, a0.dst_frame_stride, kTileW * 3,
-                      M::kTileH))
-        return VR180_ERR_UNSUPPORTED;
+    key.rows = a0.view[0].rows;
+    key.cols = a0.view[0].cols;
+    key.n_views = a0.n_views;
+    key.n_frames = a0.n_frames;
+    key.H = a0.H;
+    key.mode = M::kInterp;
+    key.dst = a0.dst;
+    key.dst_pitch = a0.dst_pitch;
+    key.dst_fs = a0.dst_frame_stride;
+    static thread_local Key cached_key;
+    static thread_local TmaMaps cached_tm;
+    static thread_local bool cached = false;
+    if (!cached || memcmp(&key, &cached_key, sizeof(key)) != 0) {
+        cached = false;
+        TmaMaps& t = cached_tm;
+        memset(&t, 0, sizeof(t));
+        for (int v = 0; v < a0.n_views; ++v) {
+            const ViewArgs& vw = a0.view[v];
+            for (int w = 0; w < 2; ++w)
+                for (int r = 0; r < kRowSizes; ++r)
+                    if (!encode_u8_3d(&t.src[v][w][r], vw.src, (long long)vw.cols * 3, vw.rows, a0.n_frames, vw.pitch,
+                                      vw.frame_stride, w ? kPitchWide : kPitchNarrow, M::kRowsMin + r * kRowsStep))
+                        return VR180_ERR_UNSUPPORTED;
+        }
+        if (a0.n_views == 1) memcpy(&t.src[1], &t.src[0], sizeof(t.src[0]));
+        if (!encode_u8_3d(&t.dst, a0.dst, a0.dst_pitch, a0.H, a0.n_frames, a0.dst_pitch, a0.dst_frame_stride, kTileW * 3,
+                          M::kTileH))
+            return VR180_ERR_UNSUPPORTED;
+        cached_key = key;
+        cached = true;
+    }
+    const TmaMaps& tm = cached_tm;
 
     static std::atomic<int> attr_done[64];
     int dev = 0;
