@@ -57,6 +57,10 @@ WORKLOADS = {
     "8k_cubic_auto": dict(n=4096, interp=2, tuple_=False, chain="base", src="analytic", radius="auto", pairs=16,
                           desc="batched 8K pairs, base chain, fused analytic + get_radius per frame consumed on device, "
                                "INTER_CUBIC [BASELINE configs[4]]"),
+    "8k_cubic_auto_varying": dict(n=4096, interp=2, tuple_=False, chain="base", src="analytic", radius="auto", pairs=16,
+                                  vary=True,
+                                  desc="as 8k_cubic_auto, but consecutive frames have different disc radii, so the "
+                                       "per-pixel constants are rebuilt for every frame"),
 }
 
 
@@ -141,15 +145,22 @@ def oracle_ops(kind: str, conj: bool):
             ("fisheye_dec", "equidistant")]
 
 
-def synth_frames_torch(torch, n_frames: int, n: int, seed: int, device):
-    """Synthetic fisheye frames: uniform random bytes inside the disc, zeros outside."""
+def synth_frames_torch(torch, n_frames: int, n: int, seed: int, device, vary_margin: bool = False):
+    """Synthetic fisheye frames: uniform random bytes inside the disc, zeros outside.  The bytes
+    are drawn from [16, 256) so that no pixel INSIDE the disc is "black" for get_radius (b + g + r < 30,
+    transformer.py:133): with [0, 256) about one pixel per scan line is, and radius="auto" then returns the
+    distance between two noise pixels (0.5 ...) instead of the disc radius -(R + 0.5)."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    frames = torch.randint(0, 256, (n_frames, n, n, 3), dtype=torch.uint8, device=device, generator=g)
+    frames = torch.randint(16, 256, (n_frames, n, n, 3), dtype=torch.uint8, device=device, generator=g)
     yy = torch.arange(n, device=device).view(n, 1)
     xx = torch.arange(n, device=device).view(1, n)
-    outside = ((xx - n // 2) ** 2 + (yy - n // 2) ** 2) > (n // 2 - 8) ** 2
-    frames[:, outside] = 0
+    r2 = (xx - n // 2) ** 2 + (yy - n // 2) ** 2
+    if vary_margin:  # every frame gets a different disc radius (margin 8, 12, 16, 20, 8, ...)
+        for i in range(n_frames):
+            frames[i, r2 > (n // 2 - 8 - 4 * (i % 4)) ** 2] = 0
+    else:
+        frames[:, r2 > (n // 2 - 8) ** 2] = 0
     return frames
 
 
@@ -182,7 +193,7 @@ def cpu_reference_setup(wl: dict, sample_pairs: int):
     yy, xx = np.ogrid[:n, :n]
     outside = (xx - n // 2) ** 2 + (yy - n // 2) ** 2 > (n // 2 - 8) ** 2
     for i in range(2 * sample_pairs):
-        img = np.random.default_rng(i).integers(0, 256, (n, n, 3), dtype=np.uint8)
+        img = np.random.default_rng(i).integers(16, 256, (n, n, 3), dtype=np.uint8)
         img[outside] = 0
         rng_frames.append(img)
     t0 = time.perf_counter()
@@ -274,8 +285,8 @@ def run_workload(torch, V, wl_name: str, wl: dict, steps: int, warmup: int, dist
     radius = "auto" if wl["radius"] == "auto" else n / 2
     wp = V.SbsWarper(t, size_input=(n, n), size_output=(n, n), interpolation=wl["interp"], radius=radius,
                      map_source=wl["src"], device=device)
-    left = synth_frames_torch(torch, pairs * ring, n, 1, device)
-    right = synth_frames_torch(torch, pairs * ring, n, 2, device)
+    left = synth_frames_torch(torch, pairs * ring, n, 1, device, vary_margin=wl.get("vary", False))
+    right = synth_frames_torch(torch, pairs * ring, n, 2, device, vary_margin=wl.get("vary", False))
     out = torch.empty((pairs * ring, n, 2 * n, 3), dtype=torch.uint8, device=device)
     if wl["src"] != "analytic":
         wp.fixed_lut() if wl["src"] == "lut_fixed" else wp.maps()
@@ -315,7 +326,7 @@ def run_workload(torch, V, wl_name: str, wl: dict, steps: int, warmup: int, dist
         import ctypes as C
 
         N = V._native
-        pe = min(pairs, 8)
+        pe = min(pairs, 16)
         nbytes_in, nbytes_out = pe * n * n * 3, pe * n * 2 * n * 3
         ptrs = []
         for nb in (nbytes_in, nbytes_in, nbytes_out):

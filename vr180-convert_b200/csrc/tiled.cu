@@ -338,24 +338,37 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
 
     int st = 0;
     uint32_t ph = 0;
+    typename M::Pixel cur[M::kPx];  // DYN: constants of the current radius
+    double cur_rad = CUDART_NAN;
+    bool cur_have = false;
+#pragma unroll
+    for (int k = 0; k < M::kPx; ++k) cur[k] = pc[k];
     for (int n = 0; n < n_items; ++n) {
         mbar_wait(s_full + st * 8, ph);
         const uint8_t* buf = smem + st * stage_bytes;
         uint32_t res[M::kPx];
         if (DYN) {
+            // The per-pixel constants depend on the frame only through its radius: they are rebuilt when the radius
+            // changes (a static rig gives runs of equal radii; both eyes of a frame always share it).
             const int f = f0 + ((NV == 2) ? (n >> 1) : n);
             const double rad = __ldg(dr.radius + f);
-            const int2 org = s_org[st];
-            const bool have = rad == rad;
+            if (!(rad == cur_rad)) {
+                const int2 org = s_org[st];
+                cur_have = rad == rad;
+#pragma unroll
+                for (int k = 0; k < M::kPx; ++k) {
+                    const int qx = denorm_q(nx[k], rad, dr.cx), qy = denorm_q(ny[k], rad, dr.cy);
+                    const int off = ((qy >> kInterBits) - M::kLo - org.y) * PITCH + 3 * ((qx >> kInterBits) - M::kLo) - org.x;
+                    cur[k].boff = cur_have ? (off & ~3) : 0;
+                    cur[k].sh = (off & 3) * 8;
+                    M::weights(cur[k], qx & 31, qy & 31, tab);
+                }
+                cur_rad = rad;
+            }
 #pragma unroll
             for (int k = 0; k < M::kPx; ++k) {
-                typename M::Pixel px;
-                const int qx = denorm_q(nx[k], rad, dr.cx), qy = denorm_q(ny[k], rad, dr.cy);
-                const int off = ((qy >> kInterBits) - M::kLo - org.y) * PITCH + 3 * ((qx >> kInterBits) - M::kLo) - org.x;
-                px.boff = have ? (off & ~3) : 0;
-                px.sh = (off & 3) * 8;
-                M::weights(px, qx & 31, qy & 31, tab);
-                res[k] = have ? M::template sample<PITCH>(buf, px) : 0u;
+                const uint32_t r = M::template sample<PITCH>(buf, cur[k]);
+                res[k] = cur_have ? r : 0u;  // NaN radius (no transition found): border colour
             }
         } else {
 #pragma unroll
