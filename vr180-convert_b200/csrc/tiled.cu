@@ -42,17 +42,20 @@
 namespace vr180 {
 namespace tiled {
 
-constexpr int kTileW = 32;      // output tile width; a warp covers an 8 x 4 pixel patch per step (lane & 7 = column,
-                                // lane >> 3 = row): its source footprint is a compact 2-D patch whatever the local
-                                // direction of the map, which keeps the tap loads (nearly) free of bank conflicts
+constexpr int kTileW = 32;      // output tile width.  Per step a warp covers 32 pixels: one output row (bilinear: the
+                                // taps of a row are ~26 consecutive source pixels = ~20 consecutive words, one
+                                // wavefront per load while the row stays in one source row) or an 8 x 4 patch (bicubic)
 constexpr int kSamplers = 256;  // 8 sampling warps
 constexpr int kThreads = kSamplers + 32;  // + the TMA producer warp
 constexpr int kMaxStages = 8;   // ring depth is chosen per tile: kStageArea / (bytes of the tile's source rectangle)
 constexpr int kRowsStep = 8, kRowSizes = 5;  // TMA load box heights: Mode::kRowsMin + 8 r, r < 5
-constexpr int kPitchNarrow = 160, kPitchWide = 224;  // staged row pitch = TMA box width (bytes).  40 / 56 words =
-                                // +8 / -8 banks per row, so the <= 8-word row segments of a patch's 4 source rows
-                                // fall into disjoint banks
-constexpr int kStageArea = 40960;  // >= 2 stages of the largest admissible rectangle (64 rows x 224 B)
+// Staged row pitch = TMA box width (bytes), a multiple of 16 picked PER TILE: the smallest kPitchCands widths that
+// hold the tile's source rectangle are compared by the bank conflicts of the tile's own tap addresses (counted with
+// match.any in the prologue) plus the shared-memory wavefronts of the TMA write of the box itself.
+constexpr int kPitchMin = 96, kPitchMax = 256, kPitchStep = 16;
+constexpr int kWidths = (kPitchMax - kPitchMin) / kPitchStep + 1;  // 11 box widths
+constexpr int kPitchCands = 4;
+constexpr int kStageArea = 40960;  // >= 2 stages of the largest admissible rectangle (64 rows x 256 B)
 constexpr int kOutBufs = 4;        // power of two
 constexpr int kOutArea = kOutBufs * 32 * kTileW * 3;
 constexpr int kOffOut = kStageArea;
@@ -77,13 +80,14 @@ struct StdChain {
 struct TiledParams {
     int tiles_x;
     int sep_prefix;  // generic chains only: ops[0..1] = Normalize, EquirectangularEncoder
+    int debug;       // VR180_TILED_DEBUG: bit 0 = legacy pitches (160 / 224 bytes, no per-tile choice)
     const short* tab;  // bicubic: OpenCV's 1024 x 16 int16 weight table (device)
     StdChain std[2];
 };
 
 // TMA descriptors of one launch (kernel parameter; the TMA unit reads them from the parameter bank).
 struct alignas(64) TmaMaps {
-    CUtensorMap src[2][2][kRowSizes];  // [view][0: 160-byte, 1: 224-byte boxes][box rows kRowsMin + 8 r]: uint8 (cols * 3, rows, frames)
+    CUtensorMap src[2][kWidths][kRowSizes];  // [view][box bytes kPitchMin + 16 w][box rows kRowsMin + 8 r]: uint8 (cols * 3, rows, frames)
     CUtensorMap dst;                   // uint8 (dst_pitch, H, frames), box (96, tile height, 1)
 };
 
@@ -132,6 +136,25 @@ __device__ __forceinline__ void bulk_wait_read() {  // all but the N newest bulk
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
+// The 2 x 12-byte tap windows of a bilinear pixel (rows q0 and q1, shared-window addresses).  Only a byte offset of
+// 3 (sh == 24) reaches into the third word: the other lanes skip that load (fewer active lanes = fewer bank
+// conflicts) and leave a2 / b2 undefined -- the funnel shifts below never look at them for sh < 24.
+// volatile: the same shared address holds another frame after every barrier wait.
+__device__ __forceinline__ void lds_taps(uint32_t q0, uint32_t q1, int sh, uint32_t& a0, uint32_t& a1, uint32_t& a2,
+                                         uint32_t& b0, uint32_t& b1, uint32_t& b2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.eq.s32 p, %8, 24;\n\t"
+        "ld.shared.u32 %0, [%6];\n\t"
+        "ld.shared.u32 %1, [%6+4];\n\t"
+        "ld.shared.u32 %3, [%7];\n\t"
+        "ld.shared.u32 %4, [%7+4];\n\t"
+        "@p ld.shared.u32 %2, [%6+8];\n\t"
+        "@p ld.shared.u32 %5, [%7+8];\n\t}"
+        : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(b0), "=r"(b1), "=r"(b2)
+        : "r"(q0), "r"(q1), "r"(sh));
+}
+
 __device__ __forceinline__ uint32_t dp2a_lo_su(uint32_t w, uint32_t px, uint32_t acc) {  // s16 x u8, bytes 0..1
     uint32_t d;
     asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(acc));
@@ -149,6 +172,7 @@ __device__ __forceinline__ uint32_t dp2a_hi_su(uint32_t w, uint32_t px, uint32_t
 // it), the per-pixel constants and the sampling of one pixel from the staged rectangle.
 struct Linear {
     static constexpr int kPx = 4, kTileH = 32, kLo = 0, kHi = 1, kRowsMin = 32, kInterp = VR180_INTER_LINEAR;
+    static constexpr bool kRowPatch = true;  // a warp step = 32 pixels of one output row (pixel k of a thread: row 4 band + k)
     struct Pixel {  // constant over the frames of the batch
         int boff;          // byte offset (4-aligned) of the 12-byte tap window of row 0 inside a stage buffer
         int sh;            // 8 * (tap00 byte offset & 3)
@@ -161,16 +185,12 @@ struct Linear {
         p.W23 = (uint32_t)(64 * w10) | ((uint32_t)(64 * w11) << 16);
     }
     // One output pixel from the staged rectangle: the three result bytes [c0 c1 c2 0].
-    template <int PITCH>
-    __device__ static __forceinline__ uint32_t sample(const uint8_t* buf, const Pixel& p) {
-        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(buf + p.boff);
-        const uint32_t* r1 = r0 + PITCH / 4;
+    // `sbuf`: shared-window address of the stage, `pitch`: its row pitch in bytes
+    __device__ static __forceinline__ uint32_t sample(uint32_t sbuf, const Pixel& p, uint32_t pitch) {
+        const uint32_t row0 = sbuf + (uint32_t)p.boff;
         const int sh = p.sh;
-        // the 6 tap bytes start at byte sh / 8 of the window: only an offset of 3 reaches into the third word, so
-        // 3/4 of the lanes skip that load (fewer active lanes = fewer bank conflicts)
-        const bool third = sh == 24;
-        const uint32_t a0 = r0[0], a1 = r0[1], a2 = third ? r0[2] : 0u;
-        const uint32_t b0 = r1[0], b1 = r1[1], b2 = third ? r1[2] : 0u;
+        uint32_t a0, a1, a2, b0, b1, b2;
+        lds_taps(row0, row0 + pitch, sh, a0, a1, a2, b0, b1, b2);
         // byte-align: lo = [c0 c1 c2 c0'], hi = [c1' c2' . .]  (primed = the pixel at ix + 1)
         const uint32_t r0lo = __funnelshift_r(a0, a1, sh), r0hi = __funnelshift_r(a1, a2, sh);
         const uint32_t r1lo = __funnelshift_r(b0, b1, sh), r1hi = __funnelshift_r(b1, b2, sh);
@@ -187,6 +207,7 @@ struct Linear {
 
 struct Cubic {
     static constexpr int kPx = 2, kTileH = 16, kLo = 1, kHi = 2, kRowsMin = 16, kInterp = VR180_INTER_CUBIC;
+    static constexpr bool kRowPatch = false;  // a warp step = an 8 x 4 pixel patch (pixel k of a thread: column + 8 k)
     struct Pixel {
         int boff;       // byte offset (4-aligned) of the 16-byte window of tap row 0 (iy - 1), first tap ix - 1
         int sh;
@@ -198,13 +219,13 @@ struct Cubic {
         p.w[0] = lo.x; p.w[1] = lo.y; p.w[2] = lo.z; p.w[3] = lo.w;
         p.w[4] = hi.x; p.w[5] = hi.y; p.w[6] = hi.z; p.w[7] = hi.w;
     }
-    template <int PITCH>
-    __device__ static __forceinline__ uint32_t sample(const uint8_t* buf, const Pixel& p) {
-        const uint32_t* r = reinterpret_cast<const uint32_t*>(buf + p.boff);
+    __device__ static __forceinline__ uint32_t sample(uint32_t sbuf, const Pixel& p, uint32_t pitch) {
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(
+            static_cast<const uint8_t*>(__cvta_shared_to_generic(sbuf)) + p.boff);
         const int sh = p.sh;
         uint32_t acc0 = 16384u, acc1 = 16384u, acc2 = 16384u;  // + 1 << 14 before the >> 15
 #pragma unroll
-        for (int ky = 0; ky < 4; ++ky, r += PITCH / 4) {
+        for (int ky = 0; ky < 4; ++ky, r += pitch / 4) {
             const uint32_t a0 = r[0], a1 = r[1], a2 = r[2], a3 = r[3];
             // byte-align the 12 tap bytes (taps t0..t3, channels 0..2):
             //   A0 = [t0c0 t0c1 t0c2 t1c0]  A1 = [t1c1 t1c2 t2c0 t2c1]  A2 = [t2c2 t3c0 t3c1 t3c2]
@@ -266,31 +287,37 @@ struct TileGeom {
 //                              issues the TMA store of the tile and re-fills the stage with item n + S
 //   oempty[o]  (1)             the producer arrives when the store that last used out buffer o has finished reading
 //                              it (bulk wait_group.read); the sampling warps wait before rewriting it (item n - 4)
-template <class M, int NV, int PITCH, bool DYN>
+template <class M, int NV, bool DYN, int FR>  // FR: frames per item (2: one box load / tile store / barrier round per 2 frames)
 __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm, int v_begin, int f0, int f1,
-                                           const typename M::Pixel (&pc)[M::kPx], const TileGeom& tg, uint8_t* smem,
-                                           int band, int cg, const DynRadius& dr, const double (&nx)[M::kPx],
-                                           const double (&ny)[M::kPx], const short* tab) {
+                                           const typename M::Pixel (&pc)[M::kPx], const TileGeom& tg, const int pitch,
+                                           uint8_t* smem, int band, int cg, const DynRadius& dr,
+                                           const double (&nx)[M::kPx], const double (&ny)[M::kPx], const short* tab) {
+    static_assert(FR == 1 || (FR == 2 && !DYN), "a per-frame radius gives every frame its own rectangle");
     constexpr int kOutTileBytes = M::kTileH * kTileW * 3;
+    constexpr int kOutItemBytes = FR * kOutTileBytes;
+    constexpr int OB = kOutBufs / FR;  // out buffers of one item each (the same area either way)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s_stage = smem_u32(smem), s_full = s_stage + kOffBar;
     const uint32_t s_ofull = s_full + 2 * kMaxStages * 8, s_oempty = s_ofull + kOutBufs * 8, s_out = s_stage + kOffOut;
 
     int2* const s_org = reinterpret_cast<int2*>(smem + kOffOrg);
-    const int n_items = (f1 - f0) * NV;
+    // item n = FR consecutive frames of one view; a chunk with an odd frame count ends with a phantom frame: the
+    // host keeps chunks even, so it lies past the end of the batch, where TMA loads zeros and drops the store
+    const int n_items = ((f1 - f0 + FR - 1) / FR) * NV;
     const int rsel = tg.nrows <= M::kRowsMin ? 0 : (tg.nrows - M::kRowsMin + kRowsStep - 1) / kRowsStep;
-    const int stage_bytes = (M::kRowsMin + rsel * kRowsStep) * PITCH;  // multiple of 128
+    const int rect_bytes = (M::kRowsMin + rsel * kRowsStep) * pitch;  // one frame's box; multiple of 128
+    const int stage_bytes = FR * rect_bytes;
     const int S = min(kMaxStages, kStageArea / stage_bytes);
 
     if (warp == kSamplers / 32) {  // ---- producer ----
         if (lane != 0) return;
-        const CUtensorMap* const map0 = &tm.src[v_begin][PITCH == kPitchWide ? 1 : 0][rsel];
+        const CUtensorMap* const map0 = &tm.src[v_begin][(pitch - kPitchMin) / kPitchStep][rsel];
         const int dst_x0 = (a.view[v_begin].dst_x_offset + tg.x0) * 3;
         const int dst_x1 = (a.view[v_begin + NV - 1].dst_x_offset + tg.x0) * 3;
         int p_item = 0, p_stage = 0;  // next item to fetch and its stage
         auto load = [&]() {
             const uint32_t bar = s_full + p_stage * 8;
-            const int v = (NV == 2) ? (p_item & 1) : 0, f = f0 + ((NV == 2) ? (p_item >> 1) : p_item);
+            const int v = (NV == 2) ? (p_item & 1) : 0, f = f0 + FR * ((NV == 2) ? (p_item >> 1) : p_item);
             int bx0 = tg.bx0, ry0 = tg.ry0;
             if (DYN) {  // this frame's rectangle; its origin travels to the samplers next to the stage
                 const double rad = __ldg(dr.radius + f);
@@ -306,21 +333,21 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
                 s_org[p_stage] = make_int2(bx0, ry0);  // released to the samplers by the arrive below
             }
             mbar_expect_tx(bar, (uint32_t)stage_bytes);
-            tma_load_3d(s_stage + p_stage * stage_bytes, map0 + v * (2 * kRowSizes), bx0, ry0, f, bar);
+            tma_load_3d(s_stage + p_stage * stage_bytes, map0 + v * (kWidths * kRowSizes), bx0, ry0, f, bar);
             ++p_item;
             if (++p_stage == S) p_stage = 0;
         };
         for (int n = 0; n < S && n < n_items; ++n) load();  // fill the ring
         for (int n = 0; n < n_items; ++n) {
-            const int o = n & (kOutBufs - 1);
-            const int v = (NV == 2) ? (n & 1) : 0, f = f0 + ((NV == 2) ? (n >> 1) : n);
-            mbar_wait(s_ofull + o * 8, (uint32_t)(n / kOutBufs) & 1u);  // every sampling warp has written item n
-            tma_store_3d(&tm.dst, v ? dst_x1 : dst_x0, tg.y0, f, s_out + o * kOutTileBytes);
+            const int o = n & (OB - 1);
+            const int v = (NV == 2) ? (n & 1) : 0, f = f0 + FR * ((NV == 2) ? (n >> 1) : n);
+            mbar_wait(s_ofull + o * 8, (uint32_t)(n / OB) & 1u);  // every sampling warp has written item n
+            tma_store_3d(&tm.dst, v ? dst_x1 : dst_x0, tg.y0, f, s_out + o * kOutItemBytes);
             bulk_commit();
             if (n + S < n_items) load();  // ofull(n) also means: every warp has left the stage of item n -> re-fill it
             if (n >= 1) {
                 bulk_wait_read<1>();  // the store of item n - 1 has finished reading its out buffer
-                mbar_arrive(s_oempty + ((n - 1) & (kOutBufs - 1)) * 8);
+                mbar_arrive(s_oempty + ((n - 1) & (OB - 1)) * 8);
             }
         }
         bulk_wait_read<0>();  // shared memory must stay valid until the last store has read it
@@ -328,13 +355,20 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     }
 
     // ---- sampling warps ----
-    // word j = lane & 7 (< 6) of the 24-byte row segment of this lane's patch row = bytes of pixels p0 and p0 + 1
-    const int wj = lane & 7, p0 = (4 * wj) / 3, sub = 4 * wj - 3 * p0;
+    // The 3-byte results of a warp step are re-packed into words of the dense out tile with two shuffles:
+    // 8 x 4 patch: word j = lane & 7 (< 6) of the 24-byte segment of this lane's patch row; row patch: word j = lane
+    // (< 24) of the 96-byte output row.  Either way the word holds bytes of pixels p0 and p0 + 1 of the segment.
+    const int wj = M::kRowPatch ? lane : (lane & 7), p0 = (4 * wj) / 3, sub = 4 * wj - 3 * p0;
     const uint32_t out_sel = sub == 0 ? 0x4210u : (sub == 1 ? 0x5421u : 0x6542u);
-    const int p0c = (lane & 24) + min(p0, 7), p1c = (lane & 24) + min(p0 + 1, 7);
-    const bool writer = wj < 6;
-    // this lane's word of patch k inside the dense out tile: row 4 band + (lane >> 3), byte 24 (kPx cg + k) + 4 wj
-    uint8_t* const outp = smem + kOffOut + (4 * band + (lane >> 3)) * (kTileW * 3) + M::kPx * cg * 24 + wj * 4;
+    const int seg_last = M::kRowPatch ? 31 : 7, seg_base = M::kRowPatch ? 0 : (lane & 24);
+    const int p0c = seg_base + min(p0, seg_last), p1c = seg_base + min(p0 + 1, seg_last);
+    const bool writer = wj < (M::kRowPatch ? 24 : 6);
+    // this lane's word of step k inside the dense out tile
+    //   8 x 4 patch: row 4 band + (lane >> 3), byte 24 (kPx cg + k) + 4 wj        row patch: row 4 band + k, byte 4 lane
+    constexpr int kOutStep = M::kRowPatch ? kTileW * 3 : 24;
+    uint8_t* const outp = M::kRowPatch
+                              ? smem + kOffOut + (4 * band) * (kTileW * 3) + lane * 4
+                              : smem + kOffOut + (4 * band + (lane >> 3)) * (kTileW * 3) + M::kPx * cg * 24 + wj * 4;
 
     int st = 0;
     uint32_t ph = 0;
@@ -345,12 +379,12 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     for (int k = 0; k < M::kPx; ++k) cur[k] = pc[k];
     for (int n = 0; n < n_items; ++n) {
         mbar_wait(s_full + st * 8, ph);
-        const uint8_t* buf = smem + st * stage_bytes;
-        uint32_t res[M::kPx];
+        const uint32_t buf = s_stage + st * stage_bytes;
+        uint32_t res[FR][M::kPx];
         if (DYN) {
             // The per-pixel constants depend on the frame only through its radius: they are rebuilt when the radius
             // changes (a static rig gives runs of equal radii; both eyes of a frame always share it).
-            const int f = f0 + ((NV == 2) ? (n >> 1) : n);
+            const int f = f0 + ((NV == 2) ? (n >> 1) : n);  // FR == 1
             const double rad = __ldg(dr.radius + f);
             if (!(rad == cur_rad)) {
                 const int2 org = s_org[st];
@@ -358,7 +392,7 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
 #pragma unroll
                 for (int k = 0; k < M::kPx; ++k) {
                     const int qx = denorm_q(nx[k], rad, dr.cx), qy = denorm_q(ny[k], rad, dr.cy);
-                    const int off = ((qy >> kInterBits) - M::kLo - org.y) * PITCH + 3 * ((qx >> kInterBits) - M::kLo) - org.x;
+                    const int off = ((qy >> kInterBits) - M::kLo - org.y) * pitch + 3 * ((qx >> kInterBits) - M::kLo) - org.x;
                     cur[k].boff = cur_have ? (off & ~3) : 0;
                     cur[k].sh = (off & 3) * 8;
                     M::weights(cur[k], qx & 31, qy & 31, tab);
@@ -367,25 +401,32 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
             }
 #pragma unroll
             for (int k = 0; k < M::kPx; ++k) {
-                const uint32_t r = M::template sample<PITCH>(buf, cur[k]);
-                res[k] = cur_have ? r : 0u;  // NaN radius (no transition found): border colour
+                const uint32_t r = M::sample(buf, cur[k], (uint32_t)pitch);
+                res[0][k] = cur_have ? r : 0u;  // NaN radius (no transition found): border colour
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < M::kPx; ++k) res[k] = M::template sample<PITCH>(buf, pc[k]);
-        }
-        uint32_t word[M::kPx];
+            for (int fr = 0; fr < FR; ++fr)
 #pragma unroll
-        for (int k = 0; k < M::kPx; ++k) {
-            const uint32_t pa = __shfl_sync(0xffffffffu, res[k], p0c);
-            const uint32_t pb = __shfl_sync(0xffffffffu, res[k], p1c);
-            word[k] = __byte_perm(pa, pb, out_sel);
+                for (int k = 0; k < M::kPx; ++k) res[fr][k] = M::sample(buf + fr * rect_bytes, pc[k], (uint32_t)pitch);
         }
-        const int o = n & (kOutBufs - 1);
-        if (n >= kOutBufs) mbar_wait(s_oempty + o * 8, (uint32_t)(n / kOutBufs + 1) & 1u);  // store n - 4 has read out[o]
+        uint32_t word[FR][M::kPx];
+#pragma unroll
+        for (int fr = 0; fr < FR; ++fr)
+#pragma unroll
+            for (int k = 0; k < M::kPx; ++k) {
+                const uint32_t pa = __shfl_sync(0xffffffffu, res[fr][k], p0c);
+                const uint32_t pb = __shfl_sync(0xffffffffu, res[fr][k], p1c);
+                word[fr][k] = __byte_perm(pa, pb, out_sel);
+            }
+        const int o = n & (OB - 1);
+        if (n >= OB) mbar_wait(s_oempty + o * 8, (uint32_t)(n / OB + 1) & 1u);  // store n - OB has read out[o]
         if (writer) {
 #pragma unroll
-            for (int k = 0; k < M::kPx; ++k) *reinterpret_cast<uint32_t*>(outp + o * kOutTileBytes + k * 24) = word[k];
+            for (int fr = 0; fr < FR; ++fr)
+#pragma unroll
+                for (int k = 0; k < M::kPx; ++k)
+                    *reinterpret_cast<uint32_t*>(outp + o * kOutItemBytes + fr * kOutTileBytes + k * kOutStep) = word[fr][k];
         }
         fence_proxy_async();
         __syncwarp();
@@ -394,7 +435,8 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     }
 }
 
-template <class M, bool DYN>  // DYN: per-frame radius from device memory (vr180_mapsrc_t::radius_dev)
+// DYN: per-frame radius from device memory (vr180_mapsrc_t::radius_dev); FR: frames per pipeline item
+template <class M, bool DYN, int FR>
 __global__ void __launch_bounds__(kThreads, 4)
 k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_chain_t chain0,
              const __grid_constant__ vr180_chain_t chain1, const __grid_constant__ TiledParams tp,
@@ -418,6 +460,8 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy (TMA)
     }
+    int* const s_cost = reinterpret_cast<int*>(smem + kOffExt);  // !DYN: wavefront cost of each candidate pitch
+    if (!DYN && tid < kPitchCands) s_cost[tid] = 0;
     const int tx = blockIdx.x % tp.tiles_x, ty = blockIdx.x / tp.tiles_x;
     const int x0 = tx * kTileW, y0 = ty * M::kTileH;
     const int g = blockIdx.y;  // map group: the view whose coordinates drive this CTA
@@ -426,9 +470,10 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     const int f0 = blockIdx.z * a.frames_per_cta, f1 = min(a.n_frames, f0 + a.frames_per_cta);
     const bool sampler = warp < kSamplers / 32;  // the last warp = TMA producer: no pixels of its own
     const int sw = warp & (kSamplers / 32 - 1), band = sw / kWarpsPerBand, cg = sw % kWarpsPerBand;
-    // pixel k of this thread: column lx + 8 k, row ly
-    const int lx = 8 * kPx * cg + (lane & 7), ly = 4 * band + (lane >> 3);
-    const int j = y0 + ly;
+    // pixel k of this thread (tile-local): 8 x 4 patches: column lx + 8 k, row ly; row patches: column lane, row 4 band + k
+    const int lx = M::kRowPatch ? lane : 8 * kPx * cg + (lane & 7), ly = M::kRowPatch ? 4 * band : 4 * band + (lane >> 3);
+    auto pcol = [&](int k) { return M::kRowPatch ? lx : lx + 8 * k; };
+    auto prow = [&](int k) { return M::kRowPatch ? ly + k : ly; };
     const bool full_tile = (x0 + kTileW <= a.W) && (y0 + M::kTileH <= a.H);
 
     // ---- coordinates of this thread's pixels --------------------------------------------------------------
@@ -459,9 +504,9 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
             }
             __syncthreads();
             const bool lat_is_y = ch.ops[1].iparam != 0;
-            const double s_row = s_trig[64 + ly], c_row = s_trig[96 + ly];
             auto seed = [&](int k, ChainState& s) {
-                const double s_col = s_trig[lx + 8 * k], c_col = s_trig[32 + lx + 8 * k];
+                const double s_row = s_trig[64 + prow(k)], c_row = s_trig[96 + prow(k)];
+                const double s_col = s_trig[pcol(k)], c_col = s_trig[32 + pcol(k)];
                 s.mode = MODE_VEC3;
                 s.x = s.y = s.r = s.ux = s.uy = 0.0;
                 if (lat_is_y) {  // lat from the row, lon from the column
@@ -516,8 +561,8 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
 #pragma unroll 1
             for (int k = 0; k < kPx; ++k) {
                 double xs, ys;
-                if (dyn) eval_chain_normalised(ch, x0 + lx + 8 * k, j, xs, ys);
-                else eval_chain(ch, x0 + lx + 8 * k, j, xs, ys);
+                if (dyn) eval_chain_normalised(ch, x0 + pcol(k), y0 + prow(k), xs, ys);
+                else eval_chain(ch, x0 + pcol(k), y0 + prow(k), xs, ys);
                 const int qx = quantise(__double2float_rn(xs)), qy = quantise(__double2float_rn(ys));
 #pragma unroll
                 for (int kk = 0; kk < kPx; ++kk)
@@ -527,7 +572,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     } else if (sampler) {
 #pragma unroll
         for (int k = 0; k < kPx; ++k) {
-            const int i = x0 + lx + 8 * k;
+            const int i = x0 + pcol(k), j = y0 + prow(k);
             sx[k] = sy[k] = (int)0x80000000;
             if (i < a.W && j < a.H) {
                 if (mv.map_kind == VR180_MAPSRC_FLOAT2) {
@@ -610,7 +655,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     const int wbytes = bx1 - bx0, nrows = mxy + M::kHi + 1 - ry0;
     // Taps outside the source read TMA's zero fill = BORDER_CONSTANT(0); only unbounded footprints (NaN / huge
     // coordinates saturate to +-32768) and partial edge tiles leave the fast path.
-    bool fast = full_tile && wbytes <= kPitchWide && nrows <= M::kRowsMin + (kRowSizes - 1) * kRowsStep &&
+    bool fast = full_tile && wbytes <= kPitchMax && nrows <= M::kRowsMin + (kRowSizes - 1) * kRowsStep &&
                 mnx > -32768 && mny > -32768 && mxx < 32767 && mxy < 32767;
     int dyn_wbytes = 0, dyn_nrows = 0;
     if (dyn) {
@@ -645,16 +690,16 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         dyn_wbytes = __reduce_max_sync(0xffffffffu, dyn_wbytes);
         dyn_nrows = __reduce_max_sync(0xffffffffu, dyn_nrows);
         ok = __all_sync(0xffffffffu, ok);
-        fast = full_tile && ok && !nan_px && dyn_wbytes <= kPitchWide &&
+        fast = full_tile && ok && !nan_px && dyn_wbytes <= kPitchMax &&
                dyn_nrows <= M::kRowsMin + (kRowSizes - 1) * kRowsStep;
     }
 
     if (!fast) {  // per-pixel gather from global memory with full border handling (rare tiles)
-        if (sampler && j < a.H) {
+        if (sampler) {
 #pragma unroll
             for (int k = 0; k < kPx; ++k) {
-                const int i = x0 + lx + 8 * k;
-                if (i < a.W) {
+                const int i = x0 + pcol(k), j = y0 + prow(k);
+                if (i < a.W && j < a.H) {
                     for (int f = f0; f < f1; ++f) {
                         uint8_t* drow = a.dst + (long long)f * a.dst_frame_stride + (long long)j * a.dst_pitch;
                         int qx = sx[k], qy = sy[k];
@@ -683,8 +728,44 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         return;
     }
 
+    // ---- row pitch of the stages = TMA box width ------------------------------------------------------------
+    // Candidates: the kPitchCands smallest multiples of 16 bytes that hold the rectangle.  Cost of a candidate in
+    // shared-memory wavefronts per (frame, eye) item: the tap loads (every sampling warp measures the wavefronts
+    // = max distinct words per bank, counted with match.any, of the first tap load of its step k = 0; a tile has
+    // 32 steps of ~6 loads with the same address pattern) + the TMA write of the box (128 bytes per wavefront).
+    int pitch = max(dyn ? dyn_wbytes : wbytes, kPitchMin);
+    if (tp.debug & 1) pitch = pitch <= 160 ? 160 : (pitch <= 224 ? 224 : 256);
+    if (!dyn) {
+        const int box_rows = M::kRowsMin + (nrows <= M::kRowsMin ? 0 : (nrows - M::kRowsMin + kRowsStep - 1) / kRowsStep) * kRowsStep;
+        if (sampler) {
+            const int row = (sy[0] >> kInterBits) - M::kLo - ry0, col = 3 * ((sx[0] >> kInterBits) - M::kLo) - bx0;
+            int cost = 0;
+#pragma unroll
+            for (int e = 0; e < kPitchCands; ++e) {
+                const int w = (row * (pitch + kPitchStep * e) + col) >> 2;
+                const unsigned same = __match_any_sync(0xffffffffu, w);
+                const bool leader = (__ffs(same) - 1) == lane;  // one lane per distinct word
+                const unsigned lm = __ballot_sync(0xffffffffu, leader);
+                int deg = 0;
+                if (leader) deg = __popc(__match_any_sync(lm, w & 31));
+                deg = __reduce_max_sync(0xffffffffu, deg);
+                if (lane == e) cost = deg;
+            }
+            constexpr int kLoadsPerTile = 32 / (kSamplers / 32) * (M::kInterp == VR180_INTER_LINEAR ? 6 : 16);
+            if (lane < kPitchCands) atomicAdd(&s_cost[lane], cost * kLoadsPerTile);
+        }
+        __syncthreads();
+        int best = 0, best_cost = INT_MAX;
+#pragma unroll
+        for (int e = 0; e < kPitchCands; ++e) {
+            const int pe = pitch + kPitchStep * e;
+            const int c = s_cost[e] + box_rows * pe / 128;
+            if (pe <= kPitchMax && c < best_cost) { best_cost = c; best = e; }
+        }
+        if (!(tp.debug & 1)) pitch += kPitchStep * best;
+    }
+
     // ---- per-pixel constants of the frame loop ------------------------------------------------------------
-    const int pitch = (dyn ? dyn_wbytes : wbytes) <= kPitchNarrow ? kPitchNarrow : kPitchWide;
     typename M::Pixel pc[kPx];
 #pragma unroll
     for (int k = 0; k < kPx; ++k) {
@@ -700,11 +781,8 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     tg.ry0 = ry0;
     tg.x0 = x0;
     tg.y0 = y0;
-#define VR180_LOOP(NV_, PITCH_, DYN_) \
-    frame_loop<M, NV_, PITCH_, DYN_>(a, tm, v_begin, f0, f1, pc, tg, smem, band, cg, dr, nx, ny, tp.tab)
-    if (pitch == kPitchNarrow) { if (nv == 2) VR180_LOOP(2, kPitchNarrow, DYN); else VR180_LOOP(1, kPitchNarrow, DYN); }
-    else                       { if (nv == 2) VR180_LOOP(2, kPitchWide, DYN);   else VR180_LOOP(1, kPitchWide, DYN); }
-#undef VR180_LOOP
+    if (nv == 2) frame_loop<M, 2, DYN, FR>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
+    else         frame_loop<M, 1, DYN, FR>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
 }
 
 }  // namespace tiled
@@ -755,20 +833,27 @@ static EncodeTiledFn encode_tiled_fn() {
 // uint8 tensor (row_bytes, rows, frames) with byte strides (pitch, frame_stride); box (box_w, box_h, 1).
 // Out-of-bounds box elements are filled with zeros on loads and dropped on stores.
 static bool encode_u8_3d(CUtensorMap* out, const void* base, long long row_bytes, long long rows, long long frames,
-                         long long pitch, long long frame_stride, int box_w, int box_h) {
+                         long long pitch, long long frame_stride, int box_w, int box_h, int box_d) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;
     if (frames <= 1 || frame_stride < pitch * rows) frame_stride = ((pitch * rows + 15) / 16) * 16;  // unused when frames == 1
     const cuuint64_t dims[3] = {(cuuint64_t)row_bytes, (cuuint64_t)rows, (cuuint64_t)(frames < 1 ? 1 : frames)};
     const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
-    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_d};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <class M, bool DYN>
+// frames per CTA: the coordinates are evaluated once per CTA, so keep the chunk as large as the grid allows
+static int frames_per_cta(long long tiles, int n_frames) {
+    int fpc = n_frames;
+    while (fpc > 1 && tiles * ((n_frames + fpc - 1) / fpc) < 148LL * 4 * 2) fpc = (fpc + 1) / 2;
+    return fpc;
+}
+
+template <class M, bool DYN, int FR>
 static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180_chain_t& c1, const short* tab,
                        cudaStream_t st) {
     using namespace tiled;
@@ -807,15 +892,15 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
         memset(&t, 0, sizeof(t));
         for (int v = 0; v < a0.n_views; ++v) {
             const ViewArgs& vw = a0.view[v];
-            for (int w = 0; w < 2; ++w)
+            for (int w = 0; w < kWidths; ++w)
                 for (int r = 0; r < kRowSizes; ++r)
                     if (!encode_u8_3d(&t.src[v][w][r], vw.src, (long long)vw.cols * 3, vw.rows, a0.n_frames, vw.pitch,
-                                      vw.frame_stride, w ? kPitchWide : kPitchNarrow, M::kRowsMin + r * kRowsStep))
+                                      vw.frame_stride, kPitchMin + w * kPitchStep, M::kRowsMin + r * kRowsStep, FR))
                         return VR180_ERR_UNSUPPORTED;
         }
         if (a0.n_views == 1) memcpy(&t.src[1], &t.src[0], sizeof(t.src[0]));
         if (!encode_u8_3d(&t.dst, a0.dst, a0.dst_pitch, a0.H, a0.n_frames, a0.dst_pitch, a0.dst_frame_stride, kTileW * 3,
-                          M::kTileH))
+                          M::kTileH, FR))
             return VR180_ERR_UNSUPPORTED;
         cached_key = key;
         cached = true;
@@ -826,7 +911,7 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
     int dev = 0;
     VR180_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !attr_done[dev].load(std::memory_order_acquire)) {
-        VR180_CUDA(cudaFuncSetAttribute(k_warp_tiled<M, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        VR180_CUDA(cudaFuncSetAttribute(k_warp_tiled<M, DYN, FR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_done[dev].store(1, std::memory_order_release);
     }
 
@@ -836,10 +921,11 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
     const int tiles_x = (a.W + kTileW - 1) / kTileW, tiles_y = (a.H + M::kTileH - 1) / M::kTileH;
     tp.tiles_x = tiles_x;
     tp.tab = tab;
+    static const int debug = [] { const char* e = getenv("VR180_TILED_DEBUG"); return e ? atoi(e) : 0; }();
+    tp.debug = debug;
     const long long tiles = (long long)tiles_x * tiles_y * n_groups;
-    // frames per CTA: the coordinates are evaluated once per CTA, so keep the chunk as large as the grid allows
-    int fpc = a.n_frames;
-    while (fpc > 1 && tiles * ((a.n_frames + fpc - 1) / fpc) < 148LL * 4 * 2) fpc = (fpc + 1) / 2;
+    int fpc = frames_per_cta(tiles, a.n_frames);
+    if (FR == 2 && (fpc & 1)) ++fpc;  // chunks start at even frames: a phantom frame can only lie past the batch
     a.frames_per_cta = fpc;
     const int chunks = (a.n_frames + fpc - 1) / fpc;
     if (chunks > 65535 || tiles_x * (long long)tiles_y > 0x7fffffffLL) return VR180_ERR_UNSUPPORTED;
@@ -854,7 +940,7 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
         match_std_chain(c, tp.std[a.view[g].chain_idx ? 1 : 0]);
     }
     dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)n_groups, (unsigned)chunks);
-    k_warp_tiled<M, DYN><<<grid, kThreads, kSmemBytes, st>>>(a, c0, c1, tp, tm);
+    k_warp_tiled<M, DYN, FR><<<grid, kThreads, kSmemBytes, st>>>(a, c0, c1, tp, tm);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     VR180_CUDA(cudaGetLastError());
     return VR180_OK;
@@ -876,6 +962,10 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
             return VR180_ERR_UNSUPPORTED;
         if (a0.n_frames > 1 && vw.frame_stride < vw.pitch * vw.rows) return VR180_ERR_UNSUPPORTED;
         if (vw.rows != a0.view[0].rows || vw.cols != a0.view[0].cols) return VR180_ERR_UNSUPPORTED;
+        // a TMA box must start at a 16-byte aligned global address: tile columns are multiples of 32 pixels (96
+        // bytes), so the eye's column offset inside the SBS frame has to be one too (an unaligned start traps
+        // with "illegal instruction" on B200, for loads and stores alike)
+        if ((vw.dst_x_offset * 3) & 15) return VR180_ERR_UNSUPPORTED;
     }
     if (((uintptr_t)a0.dst & 15) || (a0.dst_pitch & 15) || (a0.dst_frame_stride & 15)) return VR180_ERR_UNSUPPORTED;
     if (a0.n_frames > 1 && a0.dst_frame_stride < a0.dst_pitch * a0.H) return VR180_ERR_UNSUPPORTED;
@@ -885,12 +975,19 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
         n_dyn += (a0.view[g].map_kind == VR180_MAPSRC_ANALYTIC && a0.view[g].radius_dev) ? 1 : 0;
     if (n_dyn != 0 && n_dyn != n_groups) return VR180_ERR_UNSUPPORTED;
     const bool dyn = n_dyn != 0;
-    if (interp == VR180_INTER_LINEAR)
-        return dyn ? launch_mode<tiled::Linear, true>(a0, c0, c1, nullptr, st)
-                   : launch_mode<tiled::Linear, false>(a0, c0, c1, nullptr, st);
+    // two frames per pipeline item when the frames share their rectangles and every CTA gets at least two of them
+    const int tile_h = interp == VR180_INTER_LINEAR ? tiled::Linear::kTileH : tiled::Cubic::kTileH;
+    const long long tiles = (long long)((a0.W + tiled::kTileW - 1) / tiled::kTileW) * ((a0.H + tile_h - 1) / tile_h) * n_groups;
+    const bool pairs = !dyn && frames_per_cta(tiles, a0.n_frames) >= 2;
+    if (interp == VR180_INTER_LINEAR) {
+        if (dyn) return launch_mode<tiled::Linear, true, 1>(a0, c0, c1, nullptr, st);
+        return pairs ? launch_mode<tiled::Linear, false, 2>(a0, c0, c1, nullptr, st)
+                     : launch_mode<tiled::Linear, false, 1>(a0, c0, c1, nullptr, st);
+    }
     if (!tab_cubic) return VR180_ERR_UNSUPPORTED;
-    return dyn ? launch_mode<tiled::Cubic, true>(a0, c0, c1, tab_cubic, st)
-               : launch_mode<tiled::Cubic, false>(a0, c0, c1, tab_cubic, st);
+    if (dyn) return launch_mode<tiled::Cubic, true, 1>(a0, c0, c1, tab_cubic, st);
+    return pairs ? launch_mode<tiled::Cubic, false, 2>(a0, c0, c1, tab_cubic, st)
+                 : launch_mode<tiled::Cubic, false, 1>(a0, c0, c1, tab_cubic, st);
 }
 
 }  // namespace vr180
