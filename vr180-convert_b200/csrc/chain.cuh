@@ -170,8 +170,29 @@ __device__ __forceinline__ void op_rot3(const double* R, ChainState& s) {  // v'
 // np.polyval(np.flip(coefs_reverse), theta): y = y*x + c, highest power first
 __device__ __forceinline__ void op_poly(const double* coefs, int n, ChainState& s) {
     to_polar_nonneg(s);
+    // One uniform jump into a fully unrolled Horner chain: every coefficient is a static constant-bank operand
+    // and a step is exactly DMUL + DADD (a loop over the runtime n costs ~6 uniform address instructions per step
+    // on top of the two FP64 ones).  n <= VR180_MAX_OP_PARAMS is validated on the host.
+    static_assert(VR180_MAX_OP_PARAMS == 12, "extend the chain below");
+    const double r = s.r;
     double acc = 0.0;
-    for (int i = n - 1; i >= 0; --i) acc = add_rn(mul_rn(acc, s.r), coefs[i]);
+#define VR180_HORNER(i) acc = add_rn(mul_rn(acc, r), coefs[i]);
+    switch (n) {
+        default: VR180_HORNER(11)
+        case 11: VR180_HORNER(10)
+        case 10: VR180_HORNER(9)
+        case 9: VR180_HORNER(8)
+        case 8: VR180_HORNER(7)
+        case 7: VR180_HORNER(6)
+        case 6: VR180_HORNER(5)
+        case 5: VR180_HORNER(4)
+        case 4: VR180_HORNER(3)
+        case 3: VR180_HORNER(2)
+        case 2: VR180_HORNER(1)
+        case 1: VR180_HORNER(0)
+        case 0: break;
+    }
+#undef VR180_HORNER
     s.r = acc;
 }
 __device__ __forceinline__ void op_fisheye_dec(int mapping, ChainState& s) {

@@ -155,6 +155,10 @@ __device__ __forceinline__ void lds_taps(uint32_t q0, uint32_t q1, int sh, uint3
         : "r"(q0), "r"(q1), "r"(sh));
 }
 
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ uint32_t dp2a_lo_su(uint32_t w, uint32_t px, uint32_t acc) {  // s16 x u8, bytes 0..1
     uint32_t d;
     asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(acc));
@@ -366,9 +370,11 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     // this lane's word of step k inside the dense out tile
     //   8 x 4 patch: row 4 band + (lane >> 3), byte 24 (kPx cg + k) + 4 wj        row patch: row 4 band + k, byte 4 lane
     constexpr int kOutStep = M::kRowPatch ? kTileW * 3 : 24;
-    uint8_t* const outp = M::kRowPatch
-                              ? smem + kOffOut + (4 * band) * (kTileW * 3) + lane * 4
-                              : smem + kOffOut + (4 * band + (lane >> 3)) * (kTileW * 3) + M::kPx * cg * 24 + wj * 4;
+    uint32_t outp = s_out + (M::kRowPatch ? (4 * band) * (kTileW * 3) + lane * 4
+                                          : (4 * band + (lane >> 3)) * (kTileW * 3) + M::kPx * cg * 24 + wj * 4);
+    uint32_t flags = (writer ? 1u : 0u) | (lane == 0 ? 2u : 0u);
+    // opaque to the compiler: otherwise it re-derives them from S2R SR_TID.X inside the frame loop
+    asm volatile("" : "+r"(outp), "+r"(flags));
 
     int st = 0;
     uint32_t ph = 0;
@@ -421,16 +427,16 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
             }
         const int o = n & (OB - 1);
         if (n >= OB) mbar_wait(s_oempty + o * 8, (uint32_t)(n / OB + 1) & 1u);  // store n - OB has read out[o]
-        if (writer) {
+        if (flags & 1u) {
+            const uint32_t ob = outp + o * kOutItemBytes;
 #pragma unroll
             for (int fr = 0; fr < FR; ++fr)
 #pragma unroll
-                for (int k = 0; k < M::kPx; ++k)
-                    *reinterpret_cast<uint32_t*>(outp + o * kOutItemBytes + fr * kOutTileBytes + k * kOutStep) = word[fr][k];
+                for (int k = 0; k < M::kPx; ++k) sts32(ob + fr * kOutTileBytes + k * kOutStep, word[fr][k]);
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(s_ofull + o * 8);  // this warp's rows of item n are in out[o]; it has left stage st
+        if (flags & 2u) mbar_arrive(s_ofull + o * 8);  // this warp's rows of item n are in out[o]; it has left stage st
         if (++st == S) { st = 0; ph ^= 1u; }
     }
 }
