@@ -64,7 +64,8 @@ constexpr int kOffRed = kOffTrig + 4 * 32 * 8;
 constexpr int kOffBar = kOffRed + 8 * 4 * 4;  // full[kMaxStages], empty[kMaxStages], ofull[kOutBufs], oempty[kOutBufs]
 constexpr int kOffOrg = kOffBar + (2 * kMaxStages + 2 * kOutBufs) * 8;  // int2 origin of the rectangle in each stage
 constexpr int kOffExt = kOffOrg + kMaxStages * 8;                         // double[8][4] per-warp normalised extremes
-constexpr int kSmemBytes = kOffExt + 8 * 4 * 8;
+constexpr int kOffCost = kOffExt + 8 * 4 * 8;                             // int[kPitchCands] candidate pitch costs
+constexpr int kSmemBytes = kOffCost + 16;
 
 // The standard chain shape, lowered once on the host (see match_std_chain):
 //   Normalize, EquirectangularEncoder, [Euclidean3DRotator], [PolynomialScaler], FisheyeDecoder("equidistant"),
@@ -466,8 +467,8 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy (TMA)
     }
-    int* const s_cost = reinterpret_cast<int*>(smem + kOffExt);  // !DYN: wavefront cost of each candidate pitch
-    if (!DYN && tid < kPitchCands) s_cost[tid] = 0;
+    int* const s_cost = reinterpret_cast<int*>(smem + kOffCost);  // wavefront cost of each candidate pitch
+    if (tid < kPitchCands) s_cost[tid] = 0;
     const int tx = blockIdx.x % tp.tiles_x, ty = blockIdx.x / tp.tiles_x;
     const int x0 = tx * kTileW, y0 = ty * M::kTileH;
     const int g = blockIdx.y;  // map group: the view whose coordinates drive this CTA
@@ -593,6 +594,27 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         }
     }
 
+    // ---- per-frame radius: a chunk whose frames all share one (finite) radius is a fixed-radius chunk ----------
+    // (a static rig: get_radius returns the same value frame after frame).  Its coordinates get their Denormalize
+    // here and the tile takes the fixed-radius pipeline -- per-tile pitch choice, constants built once, no
+    // per-item radius loads; only chunks with varying radii run the per-frame-rectangle loop.
+    bool dynr = dyn;  // CTA-uniform
+    if (dyn) {
+        const vr180_chain_t& ch = mv.chain_idx ? chain1 : chain0;
+        const double r0 = __ldg(mv.radius_dev + f0);
+        int same = r0 == r0;
+        for (int f = f0 + 1 + lane; f < f1; f += 32) same &= __ldg(mv.radius_dev + f) == r0;
+        if (__all_sync(0xffffffffu, same)) {
+            dynr = false;
+            const double cx = ch.ops[ch.n_ops - 1].p[2], cy = ch.ops[ch.n_ops - 1].p[3];
+#pragma unroll
+            for (int k = 0; k < kPx; ++k) {
+                sx[k] = denorm_q(nx[k], r0, cx);
+                sy[k] = denorm_q(ny[k], r0, cy);
+            }
+        }
+    }
+
     // ---- source rectangle of the tile ---------------------------------------------------------------------
     int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
 #pragma unroll
@@ -618,7 +640,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     dr.cx = dr.cy = 0.0;
     dr.ext[0] = dr.ext[1] = dr.ext[2] = dr.ext[3] = 0.0;
     int nan_px = 0;
-    if (dyn) {  // tile extremes of the normalised coordinates (frame independent)
+    if (dynr) {  // tile extremes of the normalised coordinates (frame independent)
         double* s_ext = reinterpret_cast<double*>(smem + kOffExt);
         double e0 = CUDART_INF, e1 = -CUDART_INF, e2 = CUDART_INF, e3 = -CUDART_INF;
         if (sampler) {
@@ -664,7 +686,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     bool fast = full_tile && wbytes <= kPitchMax && nrows <= M::kRowsMin + (kRowSizes - 1) * kRowsStep &&
                 mnx > -32768 && mny > -32768 && mxx < 32767 && mxy < 32767;
     int dyn_wbytes = 0, dyn_nrows = 0;
-    if (dyn) {
+    if (dynr) {
         const double* s_ext = reinterpret_cast<const double*>(smem + kOffExt);
         dr.ext[0] = dr.ext[2] = CUDART_INF;
         dr.ext[1] = dr.ext[3] = -CUDART_INF;
@@ -709,7 +731,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                     for (int f = f0; f < f1; ++f) {
                         uint8_t* drow = a.dst + (long long)f * a.dst_frame_stride + (long long)j * a.dst_pitch;
                         int qx = sx[k], qy = sy[k];
-                        if (dyn) {
+                        if (dynr) {
                             const double rad = __ldg(dr.radius + f);
                             qx = denorm_q(nx[k], rad, dr.cx);
                             qy = denorm_q(ny[k], rad, dr.cy);
@@ -739,9 +761,10 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     // shared-memory wavefronts per (frame, eye) item: the tap loads (every sampling warp measures the wavefronts
     // = max distinct words per bank, counted with match.any, of the first tap load of its step k = 0; a tile has
     // 32 steps of ~6 loads with the same address pattern) + the TMA write of the box (128 bytes per wavefront).
-    int pitch = max(dyn ? dyn_wbytes : wbytes, kPitchMin);
+    int pitch = max(dynr ? dyn_wbytes : wbytes, kPitchMin);
     if (tp.debug & 1) pitch = pitch <= 160 ? 160 : (pitch <= 224 ? 224 : 256);
-    if (!dyn) {
+    // (not worth ~100 instructions per thread when the tile serves only a few frames: tightest box then)
+    if (!dynr && (f1 - f0) * nv >= 8) {
         const int box_rows = M::kRowsMin + (nrows <= M::kRowsMin ? 0 : (nrows - M::kRowsMin + kRowsStep - 1) / kRowsStep) * kRowsStep;
         if (sampler) {
             const int row = (sy[0] >> kInterBits) - M::kLo - ry0, col = 3 * ((sx[0] >> kInterBits) - M::kLo) - bx0;
@@ -779,16 +802,21 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         const int off = (iy - M::kLo - ry0) * pitch + 3 * (ix - M::kLo) - bx0;
         pc[k].boff = off & ~3;
         pc[k].sh = (off & 3) * 8;
-        if (sampler && !dyn) M::weights(pc[k], sx[k] & 31, sy[k] & 31, tp.tab);
+        if (sampler && !dynr) M::weights(pc[k], sx[k] & 31, sy[k] & 31, tp.tab);
     }
     TileGeom tg;
-    tg.nrows = dyn ? dyn_nrows : nrows;
+    tg.nrows = dynr ? dyn_nrows : nrows;
     tg.bx0 = bx0;
     tg.ry0 = ry0;
     tg.x0 = x0;
     tg.y0 = y0;
-    if (nv == 2) frame_loop<M, 2, DYN, FR>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
-    else         frame_loop<M, 1, DYN, FR>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
+    if (DYN && dynr) {
+        if (nv == 2) frame_loop<M, 2, DYN, 1>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
+        else         frame_loop<M, 1, DYN, 1>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
+    } else {
+        if (nv == 2) frame_loop<M, 2, false, FR>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
+        else         frame_loop<M, 1, false, FR>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
+    }
 }
 
 }  // namespace tiled
