@@ -43,13 +43,13 @@ POLY = [0, 1, -0.02, 0.003]
 
 WORKLOADS = {
     # name: (per-eye input n, output n, interpolation, per_eye_tuple, map_source, radius, default pairs per step)
-    "8k_rot_poly_linear": dict(n=4096, interp=1, tuple_=True, chain="rot_poly", src="analytic", radius="fixed", pairs=32,
+    "8k_rot_poly_linear": dict(n=4096, interp=1, tuple_=True, chain="rot_poly", src="analytic", radius="fixed", pairs=64,
                                desc="batched 8K stereo pairs (2x4096^2 -> 8192x4096), per-eye Euclidean3DRotator+"
                                     "PolynomialScaler, fused analytic warp, INTER_LINEAR [BASELINE configs[2], batched]"),
     "4k_pair_linear": dict(n=2048, interp=1, tuple_=False, chain="base", src="analytic", radius="fixed", pairs=1,
                            desc="single 4K pair (2x2048^2 -> 4096x2048), base chain, fused analytic, INTER_LINEAR "
                                 "[BASELINE configs[1]]; a ring of pairs larger than L2 is cycled"),
-    "5k7_lut_linear": dict(n=2880, interp=1, tuple_=False, chain="base", src="lut_fixed", radius="fixed", pairs=32,
+    "5k7_lut_linear": dict(n=2880, interp=1, tuple_=False, chain="base", src="lut_fixed", radius="fixed", pairs=64,
                            desc="batched 5.7K pairs (2x2880^2 -> 5760x2880), cached fixed-point LUT, INTER_LINEAR "
                                 "[BASELINE configs[3]]"),
     "8k_cubic_fixed": dict(n=4096, interp=2, tuple_=False, chain="base", src="analytic", radius="fixed", pairs=16,

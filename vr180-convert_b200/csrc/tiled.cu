@@ -360,19 +360,19 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     }
 
     // ---- sampling warps ----
-    // The 3-byte results of a warp step are re-packed into words of the dense out tile with two shuffles:
-    // 8 x 4 patch: word j = lane & 7 (< 6) of the 24-byte segment of this lane's patch row; row patch: word j = lane
-    // (< 24) of the 96-byte output row.  Either way the word holds bytes of pixels p0 and p0 + 1 of the segment.
-    const int wj = M::kRowPatch ? lane : (lane & 7), p0 = (4 * wj) / 3, sub = 4 * wj - 3 * p0;
+    // The 3-byte results [c0 c1 c2 .] of a warp step are re-packed into words of the dense out tile with ONE
+    // shuffle: every lane fetches the pixel of lane + 1; lanes 4 m + i, i < 3, then hold word 3 m + i of the row
+    // segment (12 bytes of 4 pixels = 3 words): [c0 c1 c2 c0'], [c1 c2 c0' c1'], [c2 c0' c1' c2'].
+    const int sub = lane & 3;
     const uint32_t out_sel = sub == 0 ? 0x4210u : (sub == 1 ? 0x5421u : 0x6542u);
-    const int seg_last = M::kRowPatch ? 31 : 7, seg_base = M::kRowPatch ? 0 : (lane & 24);
-    const int p0c = seg_base + min(p0, seg_last), p1c = seg_base + min(p0 + 1, seg_last);
-    const bool writer = wj < (M::kRowPatch ? 24 : 6);
+    const bool writer = sub != 3;
     // this lane's word of step k inside the dense out tile
-    //   8 x 4 patch: row 4 band + (lane >> 3), byte 24 (kPx cg + k) + 4 wj        row patch: row 4 band + k, byte 4 lane
+    //   row patch: row 4 band + k, word 3 (lane >> 2) + sub
+    //   8 x 4 patch: row 4 band + (lane >> 3), byte 24 (kPx cg + k), word 3 ((lane & 7) >> 2) + sub
     constexpr int kOutStep = M::kRowPatch ? kTileW * 3 : 24;
-    uint32_t outp = s_out + (M::kRowPatch ? (4 * band) * (kTileW * 3) + lane * 4
-                                          : (4 * band + (lane >> 3)) * (kTileW * 3) + M::kPx * cg * 24 + wj * 4);
+    uint32_t outp = s_out + (M::kRowPatch ? (4 * band) * (kTileW * 3) + (3 * (lane >> 2) + sub) * 4
+                                          : (4 * band + (lane >> 3)) * (kTileW * 3) + M::kPx * cg * 24 +
+                                                (3 * ((lane & 7) >> 2) + sub) * 4);
     uint32_t flags = (writer ? 1u : 0u) | (lane == 0 ? 2u : 0u);
     // opaque to the compiler: otherwise it re-derives them from S2R SR_TID.X inside the frame loop
     asm volatile("" : "+r"(outp), "+r"(flags));
@@ -421,11 +421,8 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
 #pragma unroll
         for (int fr = 0; fr < FR; ++fr)
 #pragma unroll
-            for (int k = 0; k < M::kPx; ++k) {
-                const uint32_t pa = __shfl_sync(0xffffffffu, res[fr][k], p0c);
-                const uint32_t pb = __shfl_sync(0xffffffffu, res[fr][k], p1c);
-                word[fr][k] = __byte_perm(pa, pb, out_sel);
-            }
+            for (int k = 0; k < M::kPx; ++k)
+                word[fr][k] = __byte_perm(res[fr][k], __shfl_down_sync(0xffffffffu, res[fr][k], 1), out_sel);
         const int o = n & (OB - 1);
         if (n >= OB) mbar_wait(s_oempty + o * 8, (uint32_t)(n / OB + 1) & 1u);  // store n - OB has read out[o]
         if (flags & 1u) {
