@@ -350,10 +350,10 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
             tma_store_3d(&tm.dst, v ? dst_x1 : dst_x0, tg.y0, f, s_out + o * kOutItemBytes);
             bulk_commit();
             if (n + S < n_items) load();  // ofull(n) also means: every warp has left the stage of item n -> re-fill it
-            if (n >= 1) {
-                bulk_wait_read<1>();  // the store of item n - 1 has finished reading its out buffer
-                mbar_arrive(s_oempty + ((n - 1) & (OB - 1)) * 8);
-            }
+            // hand the out buffer back as soon as the store has read it (the next ofull is an item time away, so
+            // the producer has nothing else to do): a sampling warp may then run OB items ahead of the slowest one
+            bulk_wait_read<0>();
+            mbar_arrive(s_oempty + o * 8);
         }
         bulk_wait_read<0>();  // shared memory must stay valid until the last store has read it
         return;
