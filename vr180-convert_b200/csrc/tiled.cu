@@ -48,7 +48,7 @@ constexpr int kTileW = 32;      // output tile width.  Per step a warp covers 32
 constexpr int kSamplers = 256;  // 8 sampling warps
 constexpr int kThreads = kSamplers + 32;  // + the TMA producer warp
 constexpr int kMaxStages = 8;   // ring depth is chosen per tile: kStageArea / (bytes of the tile's source rectangle)
-constexpr int kRowsStep = 8, kRowSizes = 5;  // TMA load box heights: Mode::kRowsMin + 8 r, r < 5
+constexpr int kRowsStep = 4, kRowSizes = 9;  // TMA load box heights: Mode::kRowsMin + 4 r, r < 9
 // Staged row pitch = TMA box width (bytes), a multiple of 16 picked PER TILE: the smallest kPitchCands widths that
 // hold the tile's source rectangle are compared by the bank conflicts of the tile's own tap addresses (counted with
 // match.any in the prologue) plus the shared-memory wavefronts of the TMA write of the box itself.
@@ -310,9 +310,10 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     // host keeps chunks even, so it lies past the end of the batch, where TMA loads zeros and drops the store
     const int n_items = ((f1 - f0 + FR - 1) / FR) * NV;
     const int rsel = tg.nrows <= M::kRowsMin ? 0 : (tg.nrows - M::kRowsMin + kRowsStep - 1) / kRowsStep;
-    const int rect_bytes = (M::kRowsMin + rsel * kRowsStep) * pitch;  // one frame's box; multiple of 128
-    const int stage_bytes = FR * rect_bytes;
-    const int S = min(kMaxStages, kStageArea / stage_bytes);
+    const int rect_bytes = (M::kRowsMin + rsel * kRowsStep) * pitch;  // one frame's box; multiple of 64
+    const int stage_bytes = FR * rect_bytes;                          // bytes one TMA box load delivers
+    const int stage_stride = (stage_bytes + 127) & ~127;              // TMA destinations are 128-byte aligned
+    const int S = min(kMaxStages, kStageArea / stage_stride);
 
     if (warp == kSamplers / 32) {  // ---- producer ----
         if (lane != 0) return;
@@ -338,7 +339,7 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
                 s_org[p_stage] = make_int2(bx0, ry0);  // released to the samplers by the arrive below
             }
             mbar_expect_tx(bar, (uint32_t)stage_bytes);
-            tma_load_3d(s_stage + p_stage * stage_bytes, map0 + v * (kWidths * kRowSizes), bx0, ry0, f, bar);
+            tma_load_3d(s_stage + p_stage * stage_stride, map0 + v * (kWidths * kRowSizes), bx0, ry0, f, bar);
             ++p_item;
             if (++p_stage == S) p_stage = 0;
         };
@@ -386,7 +387,7 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     for (int k = 0; k < M::kPx; ++k) cur[k] = pc[k];
     for (int n = 0; n < n_items; ++n) {
         mbar_wait(s_full + st * 8, ph);
-        const uint32_t buf = s_stage + st * stage_bytes;
+        const uint32_t buf = s_stage + st * stage_stride;
         uint32_t res[FR][M::kPx];
         if (DYN) {
             // The per-pixel constants depend on the frame only through its radius: they are rebuilt when the radius
