@@ -758,7 +758,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     // Candidates: the kPitchCands smallest multiples of 16 bytes that hold the rectangle.  Cost of a candidate in
     // shared-memory wavefronts per (frame, eye) item: the tap loads (every sampling warp measures the wavefronts
     // = max distinct words per bank, counted with match.any, of the first tap load of its step k = 0; a tile has
-    // 32 steps of ~6 loads with the same address pattern) + the TMA write of the box (128 bytes per wavefront).
+    // 32 steps of ~6 loads with the same address pattern) + the TMA write of the box (64 bytes per wavefront, measured).
     int pitch = max(dynr ? dyn_wbytes : wbytes, kPitchMin);
     if (tp.debug & 1) pitch = pitch <= 160 ? 160 : (pitch <= 224 ? 224 : 256);
     // (not worth ~100 instructions per thread when the tile serves only a few frames: tightest box then)
@@ -786,7 +786,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
 #pragma unroll
         for (int e = 0; e < kPitchCands; ++e) {
             const int pe = pitch + kPitchStep * e;
-            const int c = s_cost[e] + box_rows * pe / 128;
+            const int c = s_cost[e] + box_rows * pe / 64;
             if (pe <= kPitchMax && c < best_cost) { best_cost = c; best = e; }
         }
         if (!(tp.debug & 1)) pitch += kPitchStep * best;
