@@ -14,22 +14,35 @@
 //              cv::remap (sampler.cuh); per pixel only {smem offset of the first tap, byte shift, packed integer
 //              weights} stay in registers.
 //   bbox       block-wide min / max of the integer source coordinates -> the tile's source rectangle.
-//   pipeline   for every (frame, eye) item the source rectangle is fetched by ONE TMA box load
-//              (cp.async.bulk.tensor.3d over the (bytes, rows, frames) view of the source batch, completion on an
-//              mbarrier) into a ring of stages sized for this tile; a dedicated producer warp runs the loads
-//              S - 2 items ahead.  TMA's out-of-bounds zero fill IS BORDER_CONSTANT(0), so tiles that straddle the
-//              source edge stay on the fast path.  No LSU instruction touches the source in global memory.
-//   sampling   a warp samples an 8 x 4 pixel patch per step.  Bilinear: 6 LDS.32 per pixel (2 rows x 12 bytes),
-//              funnel shifts to byte-align, PRMT to pair the taps, 2 x dp2a (16-bit weight x 8-bit pixel) per
-//              channel:  (sum_t w_t p_t + 512) >> 10  ==  (sum_t 64 w_t p_t + 32768) >> 16, i.e. byte 2 of the
-//              dp2a chain.  Bicubic: 4 rows x 16-byte windows, the pixel's 16 int16 table weights (OpenCV's
-//              1024 x 16 table, tables.cuh) live in 8 registers, 2 x dp2a (s16 x u8) per channel and row,
-//              clip((acc + 16384) >> 15).
-//   store      each patch row's 8 pixels x 3 bytes are re-packed with two shuffles into 6 words of a dense output
-//              tile in shared memory; the producer writes the tile into the eye's half of the SBS frame with one
-//              TMA store (full 32-byte sectors, no STG).
+//   pitch      the row pitch of the staged rectangle = the TMA box width, a multiple of 16 bytes, is picked per
+//              tile from the 4 tightest widths: every sampling warp counts the bank conflicts of its own tap
+//              addresses under each candidate (match.any: wavefronts of a load = max distinct words per bank)
+//              and the cheapest candidate in shared-memory wavefronts (tap loads + TMA write of the box) wins.
+//   pipeline   an item = 2 consecutive frames of one eye (1 with a per-frame radius).  Its source rectangles are
+//              fetched by ONE TMA box load (cp.async.bulk.tensor.3d over the (bytes, rows, frames) view of the
+//              source batch, box depth 2, completion on an mbarrier) into a ring of stages sized for this tile;
+//              a dedicated producer warp runs the loads S - 1 items ahead.  TMA's out-of-bounds zero fill IS
+//              BORDER_CONSTANT(0), so tiles that straddle the source edge stay on the fast path.  No LSU
+//              instruction touches the source in global memory.  (A TMA box must start at a 16-byte aligned
+//              global address -- B200 traps with "illegal instruction" otherwise, for loads and stores.)
+//   sampling   bilinear: a warp step = 32 pixels of one output row: their taps are ~26 consecutive source pixels,
+//              i.e. ~20 consecutive words, one wavefront per load while the row stays inside one source row.
+//              6 LDS.32 per pixel (2 rows x 12 bytes, the third word only for a byte offset of 3), funnel shifts
+//              to byte-align, PRMT to pair the taps, 2 x dp2a (16-bit weight x 8-bit pixel) per channel:
+//              (sum_t w_t p_t + 512) >> 10  ==  (sum_t 64 w_t p_t + 32768) >> 16, i.e. byte 2 of the dp2a chain.
+//              Bicubic: a warp step = an 8 x 4 patch; 4 rows x 16-byte windows, the pixel's 16 int16 table
+//              weights (OpenCV's 1024 x 16 table, tables.cuh) live in 8 registers, 2 x dp2a (s16 x u8) per
+//              channel and row, clip((acc + 16384) >> 15).
+//   store      the 3-byte results of a step are re-packed with ONE shuffle (every lane fetches the pixel of
+//              lane + 1; lanes 4 m + i, i < 3, then hold word 3 m + i of the row segment) into a dense output
+//              tile in shared memory; the producer writes the item's tiles into the eye's half of the SBS frames
+//              with one TMA store (full 32-byte sectors, no STG) and hands the buffer back once it has been read.
 // Tiles whose footprint is unbounded (NaN / huge coordinates) or exceeds the staging buffer, and partial edge
 // tiles, take the per-pixel global-memory gather of sampler.cuh inside the same kernel.
+//
+// Measured dead ends (profiles/README.md): re-packing the staged rectangle into 4-byte pixels in shared memory
+// (the conversion costs as many wavefronts as the whole-word taps save), 3 CTAs per SM with 72 registers, 8 pitch
+// candidates, sampling warps storing straight to global memory (STG) instead of the TMA tile store.
 #include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint
 
 #include <cstdlib>
@@ -275,23 +288,26 @@ struct TileGeom {
     int x0, y0;         // output tile origin
 };
 
-// The frame loop of one tile.  Items are (frame, view) pairs in frame-major order.  NV = views sampled with this
-// CTA's coordinates (2 when both eyes share the map).
+// The frame loop of one tile.  Items are (FR consecutive frames, view) in frame-major order.  NV = views sampled
+// with this CTA's coordinates (2 when both eyes share the map).
 //
 // Warp-specialised: warps 0-7 sample, lane 0 of warp 8 drives the TMA unit and nothing else, so no sampling warp
-// ever blocks on a copy.  TMA work is kept to TWO operations per item (one load box = the whole source rectangle,
-// one store box = the whole output tile): a version with 5 load boxes + 8 per-warp store boxes per item measured
-// TMA-issue bound (~50 clk per operation, profiles/r1_v7_*).
+// ever blocks on a copy.  TMA work is kept to TWO operations per item (one load box = the source rectangles of
+// the item's frames, one store box = their output tiles): a version with 5 load boxes + 8 per-warp store boxes
+// per item measured TMA-issue bound (~50 clk per operation, profiles/r1_v7_*).  With FR = 2 the per-item
+// bookkeeping (barrier waits, ring counters, proxy fence, arrive: ~45 instructions per warp) is paid once per 8
+// pixels of a thread instead of once per 4.
 //
-// The staging area is a ring of S stages of exactly the tile's footprint (box rows x PITCH bytes), so a typical
-// bilinear tile (40 rows x 160 B = 6.4 KB) gets S = 6 and the loads run up to S - 1 items ahead of the sampling.
+// The staging area is a ring of S stages of exactly the tile's footprint (FR x box rows x pitch bytes), so a
+// typical bilinear tile (2 x 36 rows x 128 B = 9.2 KB) gets S = 4 and the loads run up to S - 1 items ahead.
 // No CTA-wide barrier; three kinds of mbarrier:
 //   full[s]    (1 + tx bytes)  the box of the item in stage s has landed; the sampling warps wait on it
-//   ofull[o]   (8)             one arrive per sampling warp when its rows of the output tile are in out buffer o
-//                              (4 deep) -- which also says the warp has left the item's stage; the producer waits,
-//                              issues the TMA store of the tile and re-fills the stage with item n + S
-//   oempty[o]  (1)             the producer arrives when the store that last used out buffer o has finished reading
-//                              it (bulk wait_group.read); the sampling warps wait before rewriting it (item n - 4)
+//   ofull[o]   (8)             one arrive per sampling warp when its rows of the item's tiles are in out buffer o
+//                              (OB = 4 / FR deep) -- which also says the warp has left the item's stage; the
+//                              producer waits, issues the TMA store and re-fills the stage with item n + S
+//   oempty[o]  (1)             the producer arrives as soon as the store that used out buffer o has finished
+//                              reading it (bulk wait_group.read); the sampling warps wait before rewriting it
+//                              (item n - OB), so a warp can run at most OB items ahead of the slowest one
 template <class M, int NV, bool DYN, int FR>  // FR: frames per item (2: one box load / tile store / barrier round per 2 frames)
 __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm, int v_begin, int f0, int f1,
                                            const typename M::Pixel (&pc)[M::kPx], const TileGeom& tg, const int pitch,
