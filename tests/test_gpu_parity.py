@@ -380,6 +380,52 @@ def test_tiled_per_frame_radius_on_device(interp, per_eye):
         assert np.array_equal(got[f], want), (interp, per_eye, f, r, int((got[f] != want).sum()))
 
 
+@pytest.mark.parametrize("interp", [1, 2])
+def test_tiled_per_frame_radius_equal_radii_take_fixed_pipeline(interp):
+    """A chunk whose frames all carry the same device radius (a static rig) is routed to the fixed-radius pipeline
+    inside the per-frame-radius kernel (csrc/tiled.cu, `dynr`): the result must be the fixed-radius result, bit for
+    bit, for an odd frame count (two-frame items leave a phantom frame) and for both interpolations."""
+    import torch
+
+    hin, win, wout, hout = 192, 224, 160, 96
+    n, r = 7, 101.5
+    q = V.from_rotation_vector([0.03, -0.02, 0.05])
+    t = V.EquirectangularEncoder() * V.Euclidean3DRotator(q) * V.PolynomialScaler([0, 1, 0.05]) * V.FisheyeDecoder("equidistant")
+    rng = np.random.default_rng(13)
+    ln = rng.integers(0, 256, (n, hin, win, 3), dtype=np.uint8)
+    rn = rng.integers(0, 256, (n, hin, win, 3), dtype=np.uint8)
+    left, right = torch.from_numpy(ln).cuda(), torch.from_numpy(rn).cuda()
+    dyn = V.SbsWarper(t, size_input=(hin, win), size_output=(wout, hout), interpolation=interp, radius="auto")
+    got = dyn(left, right, radius=torch.full((n,), r, dtype=torch.float64, device="cuda")).cpu().numpy()
+    fixed = V.SbsWarper(t, size_input=(hin, win), size_output=(wout, hout), interpolation=interp, radius=r)
+    want = fixed(left, right).cpu().numpy()
+    assert np.array_equal(got, want)
+    ops = [("equirect_enc", True), ("rot3", chain_np.quat_to_matrix(*q.components).ravel().tolist()),
+           ("poly", [0, 1, 0.05]), ("fisheye_dec", "equidistant")]
+    xm, ym = chain_np.get_map(ops, radius=r, size_input=(hin, win), size_output=(wout, hout))
+    for f in (0, n - 1):
+        ref = np.concatenate([cv2.remap(ln[f], xm, ym, interpolation=interp), cv2.remap(rn[f], xm, ym, interpolation=interp)], axis=1)
+        assert np.array_equal(got[f], ref), (interp, f)
+
+
+def test_tiled_sbs_offset_not_16_byte_aligned_takes_generic_kernel():
+    """TMA boxes must start at 16-byte aligned global addresses: an output width whose eye offset (W * 3 bytes) is
+    not a multiple of 16 is not eligible for the tiled kernel and must still be exact through the generic one."""
+    import torch
+
+    n, hin, win, wout, hout = 3, 160, 160, 200, 64  # 200 * 3 = 600 bytes: 8 mod 16
+    t = V.EquirectangularEncoder() * V.FisheyeDecoder("equidistant")
+    left = torch.from_numpy(_frames(n, hin, win, 0)).cuda()
+    right = torch.from_numpy(_frames(n, hin, win, 100)).cuda()
+    got = V.SbsWarper(t, size_input=(hin, win), size_output=(wout, hout), interpolation=1, radius=80.0)(left, right).cpu().numpy()
+    xm, ym = chain_np.get_map([("equirect_enc", True), ("fisheye_dec", "equidistant")], radius=80.0, size_input=(hin, win),
+                              size_output=(wout, hout))
+    ln, rn = left.cpu().numpy(), right.cpu().numpy()
+    for f in range(n):
+        want = np.concatenate([cv2.remap(ln[f], xm, ym, interpolation=1), cv2.remap(rn[f], xm, ym, interpolation=1)], axis=1)
+        assert np.array_equal(got[f], want), f
+
+
 # ---------------------------------------------------------------------------------------------------------
 # (6) full BASELINE sizes through size-independent properties
 # ---------------------------------------------------------------------------------------------------------
