@@ -113,6 +113,61 @@ __device__ __forceinline__ void sample_linear(const Src& s, int sx, int sy, int 
     for (int c = 0; c < C; ++c) out[c] = (w00 * t00[c] + w01 * t01[c] + w10 * t10[c] + w11 * t11[c] + 512) >> 10;
 }
 
+// s16 x u8 two-way dot products (weights are OpenCV's signed int16 table entries, pixels unsigned bytes)
+__device__ __forceinline__ int dp2a_lo_s16u8(uint32_t w, uint32_t px, int acc) {  // w.lo * px.b0 + w.hi * px.b1
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(acc));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_s16u8(uint32_t w, uint32_t px, int acc) {  // w.lo * px.b2 + w.hi * px.b3
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(acc));
+    return d;
+}
+
+// Interior K x K footprint of a 3-channel image whose rows are word-aligned: every tap row is K * 3 contiguous
+// bytes, fetched as aligned 32-bit words (K * 3 / 4 + 1 loads instead of K * 3 byte loads), byte-aligned with funnel
+// shifts, regrouped per channel with PRMT and accumulated with dp2a against the row's int16 weights (one 8- or
+// 16-byte load instead of K 2-byte loads).  The caller guarantees 3 readable bytes past the last tap of a row.
+template <int K>
+__device__ __forceinline__ void sample_tab3_words(const uint8_t* __restrict__ q, long long pitch,
+                                                  const short* __restrict__ w, int* out) {
+    constexpr int NW = K * 3 / 4;  // payload words per tap row: 3 (cubic) or 6 (Lanczos4)
+    const int sh = (int)((uintptr_t)q & 3) * 8;
+    const uint8_t* r = q - ((uintptr_t)q & 3);
+    int acc0 = 16384, acc1 = 16384, acc2 = 16384;  // + 1 << 14 before the >> 15
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky, r += pitch) {
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(r);
+        uint32_t x[NW + 1], A[NW], wv[K / 2];
+#pragma unroll
+        for (int i = 0; i <= NW; ++i) x[i] = __ldg(rw + i);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) A[i] = __funnelshift_r(x[i], x[i + 1], sh);
+        if (K == 4) {
+            const uint2 t = __ldg(reinterpret_cast<const uint2*>(w + ky * K));
+            wv[0] = t.x; wv[1] = t.y;
+        } else {
+            const uint4 t = __ldg(reinterpret_cast<const uint4*>(w + ky * K));
+            wv[0] = t.x; wv[1] = t.y; wv[K / 2 - 2] = t.z; wv[K / 2 - 1] = t.w;
+        }
+#pragma unroll
+        for (int g = 0; g < K / 4; ++g) {  // taps 4 g .. 4 g + 3 = bytes of A[3 g .. 3 g + 2]
+            const uint32_t A0 = A[3 * g], A1 = A[3 * g + 1], A2 = A[3 * g + 2];
+            const uint32_t q0 = __byte_perm(__byte_perm(A0, A1, 0x0630), A2, 0x5210);  // [t0c0 t1c0 t2c0 t3c0]
+            const uint32_t q1 = __byte_perm(__byte_perm(A0, A1, 0x0741), A2, 0x6210);  // [t0c1 t1c1 t2c1 t3c1]
+            const uint32_t q2 = __byte_perm(__byte_perm(A0, A1, 0x0052), A2, 0x7410);  // [t0c2 t1c2 t2c2 t3c2]
+            const uint32_t w01 = wv[2 * g], w23 = wv[2 * g + 1];
+            acc0 = dp2a_hi_s16u8(w23, q0, dp2a_lo_s16u8(w01, q0, acc0));
+            acc1 = dp2a_hi_s16u8(w23, q1, dp2a_lo_s16u8(w01, q1, acc1));
+            acc2 = dp2a_hi_s16u8(w23, q2, dp2a_lo_s16u8(w01, q2, acc2));
+        }
+    }
+    out[0] = max(0, min(255, acc0 >> 15));
+    out[1] = max(0, min(255, acc1 >> 15));
+    out[2] = max(0, min(255, acc2 >> 15));
+}
+
 // INTER_CUBIC (K = 4) / INTER_LANCZOS4 (K = 8): K x K taps from ix-(K/2-1), int16 weights itab[ay*32+ax][ky][kx]
 // summing to 32768, out = clip((acc + 16384) >> 15).
 template <int C, int K>
@@ -123,6 +178,11 @@ __device__ __forceinline__ void sample_tab(const Src& s, int sx, int sy, const s
     int acc[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0;
+    if (C == 3 && (unsigned)ix < (unsigned)max(s.cols - (K + 1), 0) && (unsigned)iy < (unsigned)max(s.rows - (K - 1), 0) &&
+        (((uintptr_t)s.p | (uintptr_t)s.pitch) & 3) == 0) {  // word path: needs 3 spare bytes after the last tap of a row
+        sample_tab3_words<K>(s.p + (long long)iy * s.pitch + (long long)ix * 3, s.pitch, w, out);
+        return;
+    }
     if ((unsigned)ix < (unsigned)max(s.cols - (K - 1), 0) && (unsigned)iy < (unsigned)max(s.rows - (K - 1), 0)) {
         const uint8_t* q = s.p + (long long)iy * s.pitch + (long long)ix * C;
 #pragma unroll
