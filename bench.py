@@ -54,6 +54,9 @@ WORKLOADS = {
                                 "[BASELINE configs[3]]"),
     "8k_cubic_fixed": dict(n=4096, interp=2, tuple_=False, chain="base", src="analytic", radius="fixed", pairs=16,
                            desc="batched 8K pairs, base chain, fused analytic, INTER_CUBIC, fixed radius"),
+    "8k_lanczos4_fixed": dict(n=4096, interp=4, tuple_=False, chain="base", src="analytic", radius="fixed", pairs=16,
+                              desc="batched 8K pairs, base chain, fused analytic, INTER_LANCZOS4 (the default interpolation "
+                                   "of the reference's apply(), remapper.py:330), fixed radius"),
     "8k_cubic_auto": dict(n=4096, interp=2, tuple_=False, chain="base", src="analytic", radius="auto", pairs=16,
                           desc="batched 8K pairs, base chain, fused analytic + get_radius per frame consumed on device, "
                                "INTER_CUBIC [BASELINE configs[4]]"),

@@ -307,16 +307,17 @@ def test_sbs_warper_per_eye_tuple_and_auto_radius():
         assert np.array_equal(got[f], want), f
 
 
-@pytest.mark.parametrize("interp", [1, 2])
+@pytest.mark.parametrize("interp", [1, 2, 4])
 @pytest.mark.parametrize("per_eye", [False, True])
 def test_tiled_pipeline_ring_wraparound_and_source_edges(interp, per_eye):
     """Stress of the tiled TMA pipeline (csrc/tiled.cu): an odd, long batch (stage ring, out-buffer ring and
     mbarrier phases wrap several times), a radius larger than the source so that many tiles straddle the source
-    edge (TMA zero fill == BORDER_CONSTANT 0), tiles fully outside, partial edge tiles (output 200 x 104 is not a
-    multiple of the 32 x 32 / 32 x 16 tiles), shared map (2 views per CTA) and per-eye maps (1 view per CTA)."""
+    edge (TMA zero fill == BORDER_CONSTANT 0), tiles fully outside, partial edge tiles (output 208 x 104 is not a
+    multiple of the 32 x 32 / 32 x 16 / 32 x 8 tiles; 208 * 3 bytes keeps the right eye's column offset 16-byte aligned,
+    which the TMA path needs), shared map (2 views per CTA) and per-eye maps (1 view per CTA)."""
     import torch
 
-    n, hin, win, wout, hout = 23, 192, 224, 200, 104
+    n, hin, win, wout, hout = 23, 192, 224, 208, 104
     ql, qr = V.from_rotation_vector([0.03, -0.02, 0.05]), V.from_rotation_vector([-0.03, 0.02, -0.05])
     mk = lambda q: (V.EquirectangularEncoder() * V.Euclidean3DRotator(q) * V.PolynomialScaler([0, 1, 0.05])  # noqa: E731
                     * V.FisheyeDecoder("equidistant"))
@@ -342,7 +343,7 @@ def test_tiled_pipeline_ring_wraparound_and_source_edges(interp, per_eye):
         assert np.array_equal(got[f], want), (interp, per_eye, f, int((got[f] != want).sum()))
 
 
-@pytest.mark.parametrize("interp", [1, 2])
+@pytest.mark.parametrize("interp", [1, 2, 4])
 @pytest.mark.parametrize("per_eye", [False, True])
 def test_tiled_per_frame_radius_on_device(interp, per_eye):
     """Per-frame radius consumed on the device by the tiled kernel (vr180_mapsrc_t::radius_dev): every frame has
@@ -380,7 +381,7 @@ def test_tiled_per_frame_radius_on_device(interp, per_eye):
         assert np.array_equal(got[f], want), (interp, per_eye, f, r, int((got[f] != want).sum()))
 
 
-@pytest.mark.parametrize("interp", [1, 2])
+@pytest.mark.parametrize("interp", [1, 2, 4])
 def test_tiled_per_frame_radius_equal_radii_take_fixed_pipeline(interp):
     """A chunk whose frames all carry the same device radius (a static rig) is routed to the fixed-radius pipeline
     inside the per-frame-radius kernel (csrc/tiled.cu, `dynr`): the result must be the fixed-radius result, bit for

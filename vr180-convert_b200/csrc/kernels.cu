@@ -275,6 +275,7 @@ int launch_remap(const vr180_remap_params_t* p, cudaStream_t st) {
     if (!tiled_off) {
         const short* tab_cubic = nullptr;
         if (interp == VR180_INTER_CUBIC) VR180_CUDA(cudaGetSymbolAddress((void**)&tab_cubic, g_tab_cubic));
+        if (interp == VR180_INTER_LANCZOS4) VR180_CUDA(cudaGetSymbolAddress((void**)&tab_cubic, g_tab_lanczos));
         const int rc = launch_remap_tiled(a, C, interp, *chains[0], *chains[1], tab_cubic, st);
         if (rc != VR180_ERR_UNSUPPORTED) return rc;
     }

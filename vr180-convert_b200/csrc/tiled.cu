@@ -263,6 +263,52 @@ struct Cubic {
     }
 };
 
+// INTER_LANCZOS4 (the default interpolation of the reference's apply(), remapper.py:330): 8 x 8 taps.  The 64 int16
+// weights of a pixel (OpenCV's 1024 x 64 table) do not fit the register file next to the other pixels' constants, so
+// a thread owns ONE pixel (tile 32 x 8) and re-reads its 128 bytes of weights per frame through L1 / L2; the 8 tap
+// rows are 28-byte windows of the staged rectangle.  ~300 instructions per pixel: bound by issue slots.
+struct Lanczos4 {
+    static constexpr int kPx = 1, kTileH = 8, kLo = 3, kHi = 4, kRowsMin = 16, kInterp = VR180_INTER_LANCZOS4;
+    static constexpr bool kRowPatch = false;
+    struct Pixel {
+        int boff;        // byte offset (4-aligned) of the 28-byte window of tap row 0 (iy - 3), first tap ix - 3
+        int sh;
+        const short* w;  // itab[ay][ax][ky][kx], 64 int16 (device memory)
+    };
+    __device__ static __forceinline__ void weights(Pixel& p, int ax, int ay, const short* tab) {
+        p.w = tab + (((ay << 5) | ax) << 6);
+    }
+    __device__ static __forceinline__ uint32_t sample(uint32_t sbuf, const Pixel& p, uint32_t pitch) {
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(
+            static_cast<const uint8_t*>(__cvta_shared_to_generic(sbuf)) + p.boff);
+        const int sh = p.sh;
+        uint32_t acc0 = 16384u, acc1 = 16384u, acc2 = 16384u;  // + 1 << 14 before the >> 15
+#pragma unroll
+        for (int ky = 0; ky < 8; ++ky, r += pitch / 4) {
+            uint32_t x[7], A[6];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) x[i] = r[i];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) A[i] = __funnelshift_r(x[i], x[i + 1], sh);  // 24 tap bytes, byte-aligned
+            const uint4 wv = __ldg(reinterpret_cast<const uint4*>(p.w + ky * 8));
+            const uint32_t wp[4] = {wv.x, wv.y, wv.z, wv.w};  // {kx 0, 1} {2, 3} {4, 5} {6, 7}
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {  // taps 4 g .. 4 g + 3 = the 12 bytes of A[3 g .. 3 g + 2]
+                const uint32_t A0 = A[3 * g], A1 = A[3 * g + 1], A2 = A[3 * g + 2];
+                const uint32_t q0 = __byte_perm(__byte_perm(A0, A1, 0x0630), A2, 0x5210);  // [t0c0 t1c0 t2c0 t3c0]
+                const uint32_t q1 = __byte_perm(__byte_perm(A0, A1, 0x0741), A2, 0x6210);  // [t0c1 t1c1 t2c1 t3c1]
+                const uint32_t q2 = __byte_perm(__byte_perm(A0, A1, 0x0052), A2, 0x7410);  // [t0c2 t1c2 t2c2 t3c2]
+                acc0 = dp2a_hi_su(wp[2 * g + 1], q0, dp2a_lo_su(wp[2 * g], q0, acc0));
+                acc1 = dp2a_hi_su(wp[2 * g + 1], q1, dp2a_lo_su(wp[2 * g], q1, acc1));
+                acc2 = dp2a_hi_su(wp[2 * g + 1], q2, dp2a_lo_su(wp[2 * g], q2, acc2));
+            }
+        }
+        const int c0 = min(max((int)acc0 >> 15, 0), 255), c1 = min(max((int)acc1 >> 15, 0), 255),
+                  c2 = min(max((int)acc2 >> 15, 0), 255);
+        return (uint32_t)c0 | ((uint32_t)c1 << 8) | ((uint32_t)c2 << 16);
+    }
+};
+
 // Per-frame radius (vr180_mapsrc_t::radius_dev): the chain is evaluated WITHOUT its final DenormalizeTransformer
 // once per tile; frame f then only applies  x = nx * radius[f] + cx  (transformer.py:202-203), rounds to float32
 // and quantises.  That composition is monotone in nx, so the integer bounding box of a tile in frame f follows
@@ -756,8 +802,10 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                             int px[3];
                             if (M::kInterp == VR180_INTER_LINEAR)
                                 sample_linear<3>(s, qx, qy, VR180_BORDER_CONSTANT, a.bv, px);
-                            else
+                            else if (M::kInterp == VR180_INTER_CUBIC)
                                 sample_tab<3, 4>(s, qx, qy, tp.tab, VR180_BORDER_CONSTANT, a.bv, px);
+                            else
+                                sample_tab<3, 8>(s, qx, qy, tp.tab, VR180_BORDER_CONSTANT, a.bv, px);
                             uint8_t* o = drow + (long long)(vw.dst_x_offset + i) * 3;
                             o[0] = (uint8_t)px[0];
                             o[1] = (uint8_t)px[1];
@@ -794,7 +842,8 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                 deg = __reduce_max_sync(0xffffffffu, deg);
                 if (lane == e) cost = deg;
             }
-            constexpr int kLoadsPerTile = 32 / (kSamplers / 32) * (M::kInterp == VR180_INTER_LINEAR ? 6 : 16);
+            constexpr int kStepsPerWarp = M::kTileH * kTileW / kSamplers;  // warp steps (32 pixels) of a tile, per warp
+            constexpr int kLoadsPerTile = kStepsPerWarp * (M::kInterp == VR180_INTER_LINEAR ? 6 : M::kInterp == VR180_INTER_CUBIC ? 16 : 56);
             if (lane < kPitchCands) atomicAdd(&s_cost[lane], cost * kLoadsPerTile);
         }
         __syncthreads();
@@ -999,8 +1048,10 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
 // bicubic weight table.
 int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr180_chain_t& c0, const vr180_chain_t& c1,
                        const short* tab_cubic, cudaStream_t st) {
+    // `tab_cubic`: the weight table of the requested interpolation (1024 x 16 bicubic or 1024 x 64 Lanczos4)
     if (channels != 3 || a0.border_mode != VR180_BORDER_CONSTANT) return VR180_ERR_UNSUPPORTED;
-    if (interp != VR180_INTER_LINEAR && interp != VR180_INTER_CUBIC) return VR180_ERR_UNSUPPORTED;
+    if (interp != VR180_INTER_LINEAR && interp != VR180_INTER_CUBIC && interp != VR180_INTER_LANCZOS4)
+        return VR180_ERR_UNSUPPORTED;
     if (a0.bv[0] | a0.bv[1] | a0.bv[2]) return VR180_ERR_UNSUPPORTED;  // staged tiles assume a zero border colour
     const int n_groups = a0.share_map ? 1 : a0.n_views;
     for (int v = 0; v < a0.n_views; ++v) {
@@ -1024,7 +1075,9 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
     if (n_dyn != 0 && n_dyn != n_groups) return VR180_ERR_UNSUPPORTED;
     const bool dyn = n_dyn != 0;
     // two frames per pipeline item when the frames share their rectangles and every CTA gets at least two of them
-    const int tile_h = interp == VR180_INTER_LINEAR ? tiled::Linear::kTileH : tiled::Cubic::kTileH;
+    const int tile_h = interp == VR180_INTER_LINEAR  ? tiled::Linear::kTileH
+                       : interp == VR180_INTER_CUBIC ? tiled::Cubic::kTileH
+                                                     : tiled::Lanczos4::kTileH;
     const long long tiles = (long long)((a0.W + tiled::kTileW - 1) / tiled::kTileW) * ((a0.H + tile_h - 1) / tile_h) * n_groups;
     const bool pairs = !dyn && frames_per_cta(tiles, a0.n_frames) >= 2;
     if (interp == VR180_INTER_LINEAR) {
@@ -1033,6 +1086,11 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
                      : launch_mode<tiled::Linear, false, 1>(a0, c0, c1, nullptr, st);
     }
     if (!tab_cubic) return VR180_ERR_UNSUPPORTED;
+    if (interp == VR180_INTER_LANCZOS4) {
+        if (dyn) return launch_mode<tiled::Lanczos4, true, 1>(a0, c0, c1, tab_cubic, st);
+        return pairs ? launch_mode<tiled::Lanczos4, false, 2>(a0, c0, c1, tab_cubic, st)
+                     : launch_mode<tiled::Lanczos4, false, 1>(a0, c0, c1, tab_cubic, st);
+    }
     if (dyn) return launch_mode<tiled::Cubic, true, 1>(a0, c0, c1, tab_cubic, st);
     return pairs ? launch_mode<tiled::Cubic, false, 2>(a0, c0, c1, tab_cubic, st)
                  : launch_mode<tiled::Cubic, false, 1>(a0, c0, c1, tab_cubic, st);
