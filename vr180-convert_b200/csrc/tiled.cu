@@ -474,18 +474,19 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
                 const uint32_t r = M::sample(buf, cur[k], (uint32_t)pitch);
                 res[0][k] = cur_have ? r : 0u;  // NaN radius (no transition found): border colour
             }
-        } else {
-#pragma unroll
-            for (int fr = 0; fr < FR; ++fr)
-#pragma unroll
-                for (int k = 0; k < M::kPx; ++k) res[fr][k] = M::sample(buf + fr * rect_bytes, pc[k], (uint32_t)pitch);
         }
         uint32_t word[FR][M::kPx];
 #pragma unroll
-        for (int fr = 0; fr < FR; ++fr)
+        for (int fr = 0; fr < FR; ++fr) {
+            if (!DYN) {
+#pragma unroll
+                for (int k = 0; k < M::kPx; ++k) res[fr][k] = M::sample(buf + fr * rect_bytes, pc[k], (uint32_t)pitch);
+            }
+            // re-pack frame fr right away: its shuffles are in flight while the next frame is sampled
 #pragma unroll
             for (int k = 0; k < M::kPx; ++k)
                 word[fr][k] = __byte_perm(res[fr][k], __shfl_down_sync(0xffffffffu, res[fr][k], 1), out_sel);
+        }
         const int o = n & (OB - 1);
         if (n >= OB) mbar_wait(s_oempty + o * 8, (uint32_t)(n / OB + 1) & 1u);  // store n - OB has read out[o]
         if (flags & 1u) {
