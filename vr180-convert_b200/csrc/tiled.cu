@@ -47,6 +47,7 @@
 
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "chain.cuh"
 #include "common.cuh"
@@ -957,7 +958,7 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
     using namespace tiled;
     const int n_groups = a0.share_map ? 1 : a0.n_views;
     // The descriptors depend only on the buffers' geometry: video loops call with the same buffers again and again,
-    // so the last set is kept per host thread (21 cuTensorMapEncodeTiled calls cost ~20 us).
+    // so the last few sets are kept per host thread.
     struct Key {
         const void* src[2];
         long long pitch[2], fs[2];
@@ -981,12 +982,30 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
     key.dst = a0.dst;
     key.dst_pitch = a0.dst_pitch;
     key.dst_fs = a0.dst_frame_stride;
-    static thread_local Key cached_key;
-    static thread_local TmaMaps cached_tm;
-    static thread_local bool cached = false;
-    if (!cached || memcmp(&key, &cached_key, sizeof(key)) != 0) {
-        cached = false;
-        TmaMaps& t = cached_tm;
+    // small per-thread LRU: a video loop cycles through a handful of buffers (a ring of batches), and 199
+    // cuTensorMapEncodeTiled calls cost about as much host time as a single-pair launch takes on the GPU
+    struct Entry {
+        Key key;
+        TmaMaps tm;
+        uint64_t stamp;
+    };
+    constexpr size_t kCacheEntries = 8;
+    static thread_local std::vector<Entry> cache;
+    static thread_local uint64_t clock_ = 0;
+    Entry* hit = nullptr;
+    for (Entry& e : cache)
+        if (memcmp(&key, &e.key, sizeof(key)) == 0) hit = &e;
+    if (!hit) {
+        if (cache.size() < kCacheEntries) {
+            cache.emplace_back();
+            hit = &cache.back();
+        } else {
+            hit = &cache[0];
+            for (Entry& e : cache)
+                if (e.stamp < hit->stamp) hit = &e;
+        }
+        memset(&hit->key, 0xff, sizeof(hit->key));  // invalid until every descriptor is encoded
+        TmaMaps& t = hit->tm;
         memset(&t, 0, sizeof(t));
         for (int v = 0; v < a0.n_views; ++v) {
             const ViewArgs& vw = a0.view[v];
@@ -1000,10 +1019,10 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
         if (!encode_u8_3d(&t.dst, a0.dst, a0.dst_pitch, a0.H, a0.n_frames, a0.dst_pitch, a0.dst_frame_stride, kTileW * 3,
                           M::kTileH, FR))
             return VR180_ERR_UNSUPPORTED;
-        cached_key = key;
-        cached = true;
+        hit->key = key;
     }
-    const TmaMaps& tm = cached_tm;
+    hit->stamp = ++clock_;
+    const TmaMaps& tm = hit->tm;
 
     static std::atomic<int> attr_done[64];
     int dev = 0;
