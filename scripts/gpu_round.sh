@@ -12,3 +12,13 @@ timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 tail -3 gpurun_out/${TAG}_tests.log
 head -c 1500 gpurun_out/${TAG}_bench.json; echo
 tail -3 gpurun_out/${TAG}_bench.err
+for P in 16 128; do
+  timeout 200 python bench.py --steps 10 --warmup 3 --pairs $P --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_p${P}.json 2>> gpurun_out/${TAG}_bench.err
+done
+python - <<PY
+import json
+for P in (16, 32, 128):
+    try:
+        d = json.load(open("gpurun_out/${TAG}_bench_p%d.json" % P)); print("pairs", P, d["ms_per_step"], round(d["roofline"]["frac"], 4))
+    except Exception as e: print("pairs", P, "failed", e)
+PY
