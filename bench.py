@@ -508,10 +508,20 @@ def main() -> None:
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
-    if args.impl == "reference":
-        line = run_reference(args, args.workload, WORKLOADS[args.workload])
+    # stdout carries exactly ONE line, the JSON result: whatever libraries print there while the bench runs (NCCL's
+    # version banner, for instance) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         if line:
             print(json.dumps(line), flush=True)
+
+    if args.impl == "reference":
+        emit(run_reference(args, args.workload, WORKLOADS[args.workload]))
         return
 
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:  # not under torchrun: spawn one rank per GPU ourselves
@@ -520,11 +530,10 @@ def main() -> None:
             port = s.getsockname()[1]
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(port), str(Path(__file__).resolve()), *sys.argv[1:]]
+        os.dup2(real_stdout, 1)  # the ranks do their own redirection
         raise SystemExit(subprocess.call(cmd))
 
-    line = run_gpu(args)
-    if line:
-        print(json.dumps(line), flush=True)
+    emit(run_gpu(args))
 
 
 if __name__ == "__main__":
