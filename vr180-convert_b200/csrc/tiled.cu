@@ -69,17 +69,23 @@ constexpr int kRowsStep = 4, kRowSizes = 9;  // TMA load box heights: Mode::kRow
 constexpr int kPitchMin = 96, kPitchMax = 256, kPitchStep = 16;
 constexpr int kWidths = (kPitchMax - kPitchMin) / kPitchStep + 1;  // 11 box widths
 constexpr int kPitchCands = 4;
-constexpr int kStageArea = 40960;  // >= 2 stages of the largest admissible rectangle (64 rows x 256 B)
+constexpr int kStageAreaDefault = 40960;  // >= 1 two-frame stage of the largest admissible rectangle (64 rows x 256 B)
 constexpr int kOutBufs = 4;        // power of two
-constexpr int kOutArea = kOutBufs * 32 * kTileW * 3;
-constexpr int kOffOut = kStageArea;
-constexpr int kOffTrig = kOffOut + kOutArea;
-constexpr int kOffRed = kOffTrig + 4 * 32 * 8;
-constexpr int kOffBar = kOffRed + 8 * 4 * 4;  // full[kMaxStages], empty[kMaxStages], ofull[kOutBufs], oempty[kOutBufs]
-constexpr int kOffOrg = kOffBar + (2 * kMaxStages + 2 * kOutBufs) * 8;  // int2 origin of the rectangle in each stage
-constexpr int kOffExt = kOffOrg + kMaxStages * 8;                         // double[8][4] per-warp normalised extremes
-constexpr int kOffCost = kOffExt + 8 * 4 * 8;                             // int[kPitchCands] candidate pitch costs
-constexpr int kSmemBytes = kOffCost + 16;
+// Shared-memory layout of a CTA; the staging area is a property of the interpolation mode (M::kStageArea).
+template <class M>
+struct Lay {
+    static constexpr int kStageArea = M::kStageArea;
+    static constexpr int kOutArea = kOutBufs * M::kTileH * kTileW * 3;
+    static constexpr int kOffOut = kStageArea;
+    static constexpr int kOffTrig = kOffOut + kOutArea;
+    static constexpr int kOffRed = kOffTrig + 4 * 32 * 8;
+    static constexpr int kOffBar = kOffRed + 8 * 4 * 4;  // full[kMaxStages], empty[kMaxStages], ofull[kOutBufs], oempty[kOutBufs]
+    static constexpr int kOffOrg = kOffBar + (2 * kMaxStages + 2 * kOutBufs) * 8;  // int2 origin of the rectangle in each stage
+    static constexpr int kOffExt = kOffOrg + kMaxStages * 8;                         // double[8][4] per-warp normalised extremes
+    static constexpr int kOffCost = kOffExt + 8 * 4 * 8;                             // int[kPitchCands] candidate pitch costs
+    static constexpr int kOffW = (kOffCost + 16 + 15) & ~15;  // M::kWeightSmem bytes of per-pixel weights (Lanczos4)
+    static constexpr int kSmemBytes = kOffW + M::kWeightSmem;
+};
 
 // The standard chain shape, lowered once on the host (see match_std_chain):
 //   Normalize, EquirectangularEncoder, [Euclidean3DRotator], [PolynomialScaler], FisheyeDecoder("equidistant"),
@@ -191,6 +197,7 @@ __device__ __forceinline__ uint32_t dp2a_hi_su(uint32_t w, uint32_t px, uint32_t
 // it), the per-pixel constants and the sampling of one pixel from the staged rectangle.
 struct Linear {
     static constexpr int kPx = 4, kTileH = 32, kLo = 0, kHi = 1, kRowsMin = 32, kInterp = VR180_INTER_LINEAR;
+    static constexpr int kStageArea = kStageAreaDefault, kWeightSmem = 0;
     static constexpr bool kRowPatch = true;  // a warp step = 32 pixels of one output row (pixel k of a thread: row 4 band + k)
     struct Pixel {  // constant over the frames of the batch
         int boff;          // byte offset (4-aligned) of the 12-byte tap window of row 0 inside a stage buffer
@@ -226,6 +233,7 @@ struct Linear {
 
 struct Cubic {
     static constexpr int kPx = 2, kTileH = 16, kLo = 1, kHi = 2, kRowsMin = 16, kInterp = VR180_INTER_CUBIC;
+    static constexpr int kStageArea = kStageAreaDefault, kWeightSmem = 0;
     static constexpr bool kRowPatch = false;  // a warp step = an 8 x 4 pixel patch (pixel k of a thread: column + 8 k)
     struct Pixel {
         int boff;       // byte offset (4-aligned) of the 16-byte window of tap row 0 (iy - 1), first tap ix - 1
@@ -265,19 +273,24 @@ struct Cubic {
 };
 
 // INTER_LANCZOS4 (the default interpolation of the reference's apply(), remapper.py:330): 8 x 8 taps.  The 64 int16
-// weights of a pixel (OpenCV's 1024 x 64 table) do not fit the register file next to the other pixels' constants, so
-// a thread owns ONE pixel (tile 32 x 8) and re-reads its 128 bytes of weights per frame through L1 / L2; the 8 tap
-// rows are 28-byte windows of the staged rectangle.  ~300 instructions per pixel: bound by issue slots.
+// weights of a pixel (OpenCV's 1024 x 64 table) do not fit the register file, so a thread owns ONE pixel (tile
+// 32 x 8) and its 128 bytes of weights are copied once per tile into shared memory, laid out [tap row][thread] so
+// that a warp reads 512 contiguous bytes per tap row (straight from the table every lane would touch its own cache
+// line: 32 tag look-ups per load).  The 8 tap rows are 28-byte windows of the staged rectangle.  ~300 instructions
+// and ~120 shared-memory wavefronts per pixel step.
 struct Lanczos4 {
     static constexpr int kPx = 1, kTileH = 8, kLo = 3, kHi = 4, kRowsMin = 16, kInterp = VR180_INTER_LANCZOS4;
+    static constexpr int kStageArea = 16384, kWeightSmem = kSamplers * 128;  // 16 KB of stages + 32 KB of weights
     static constexpr bool kRowPatch = false;
     struct Pixel {
         int boff;        // byte offset (4-aligned) of the 28-byte window of tap row 0 (iy - 3), first tap ix - 3
         int sh;
-        const short* w;  // itab[ay][ax][ky][kx], 64 int16 (device memory)
+        const short* w;  // itab[ay][ax][ky][kx], 64 int16 in the table (device memory)
+        uint32_t ws;     // shared-window address of the thread's staged copy of them ([tap row][thread] x 16 bytes), 0 = none
     };
     __device__ static __forceinline__ void weights(Pixel& p, int ax, int ay, const short* tab) {
         p.w = tab + (((ay << 5) | ax) << 6);
+        p.ws = 0;
     }
     __device__ static __forceinline__ uint32_t sample(uint32_t sbuf, const Pixel& p, uint32_t pitch) {
         const uint32_t* r = reinterpret_cast<const uint32_t*>(
@@ -291,7 +304,14 @@ struct Lanczos4 {
             for (int i = 0; i < 7; ++i) x[i] = r[i];
 #pragma unroll
             for (int i = 0; i < 6; ++i) A[i] = __funnelshift_r(x[i], x[i + 1], sh);  // 24 tap bytes, byte-aligned
-            const uint4 wv = __ldg(reinterpret_cast<const uint4*>(p.w + ky * 8));
+            uint4 wv;
+            if (p.ws) {
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(wv.x), "=r"(wv.y), "=r"(wv.z), "=r"(wv.w)
+                             : "r"(p.ws + ky * (kSamplers * 16)));
+            } else {
+                wv = __ldg(reinterpret_cast<const uint4*>(p.w + ky * 8));
+            }
             const uint32_t wp[4] = {wv.x, wv.y, wv.z, wv.w};  // {kx 0, 1} {2, 3} {4, 5} {6, 7}
 #pragma unroll
             for (int g = 0; g < 2; ++g) {  // taps 4 g .. 4 g + 3 = the 12 bytes of A[3 g .. 3 g + 2]
@@ -365,10 +385,10 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     constexpr int kOutItemBytes = FR * kOutTileBytes;
     constexpr int OB = kOutBufs / FR;  // out buffers of one item each (the same area either way)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t s_stage = smem_u32(smem), s_full = s_stage + kOffBar;
-    const uint32_t s_ofull = s_full + 2 * kMaxStages * 8, s_oempty = s_ofull + kOutBufs * 8, s_out = s_stage + kOffOut;
+    const uint32_t s_stage = smem_u32(smem), s_full = s_stage + Lay<M>::kOffBar;
+    const uint32_t s_ofull = s_full + 2 * kMaxStages * 8, s_oempty = s_ofull + kOutBufs * 8, s_out = s_stage + Lay<M>::kOffOut;
 
-    int2* const s_org = reinterpret_cast<int2*>(smem + kOffOrg);
+    int2* const s_org = reinterpret_cast<int2*>(smem + Lay<M>::kOffOrg);
     // item n = FR consecutive frames of one view; a chunk with an odd frame count ends with a phantom frame: the
     // host keeps chunks even, so it lies past the end of the batch, where TMA loads zeros and drops the store
     const int n_items = ((f1 - f0 + FR - 1) / FR) * NV;
@@ -376,7 +396,7 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     const int rect_bytes = (M::kRowsMin + rsel * kRowsStep) * pitch;  // one frame's box; multiple of 64
     const int stage_bytes = FR * rect_bytes;                          // bytes one TMA box load delivers
     const int stage_stride = (stage_bytes + 127) & ~127;              // TMA destinations are 128-byte aligned
-    const int S = min(kMaxStages, kStageArea / stage_stride);
+    const int S = min(kMaxStages, Lay<M>::kStageArea / stage_stride);
 
     if (warp == kSamplers / 32) {  // ---- producer ----
         if (lane != 0) return;
@@ -513,12 +533,12 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     constexpr int kPx = M::kPx;
     constexpr int kWarpsPerBand = 4 / kPx;  // a band = 4 output rows x 32 columns = 4 / kPx warps of 8 kPx columns
     extern __shared__ __align__(1024) uint8_t smem[];
-    double* s_trig = reinterpret_cast<double*>(smem + kOffTrig);  // [4][32]
-    int* s_red = reinterpret_cast<int*>(smem + kOffRed);          // [8][4]
+    double* s_trig = reinterpret_cast<double*>(smem + Lay<M>::kOffTrig);  // [4][32]
+    int* s_red = reinterpret_cast<int*>(smem + Lay<M>::kOffRed);          // [8][4]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        const uint32_t bars = smem_u32(smem + kOffBar);
+        const uint32_t bars = smem_u32(smem + Lay<M>::kOffBar);
         for (int st = 0; st < kMaxStages; ++st) {
             mbar_init(bars + st * 8, 1);                               // full: the producer + tx bytes
             mbar_init(bars + (kMaxStages + st) * 8, kSamplers / 32);  // empty: one arrive per sampling warp
@@ -529,7 +549,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy (TMA)
     }
-    int* const s_cost = reinterpret_cast<int*>(smem + kOffCost);  // wavefront cost of each candidate pitch
+    int* const s_cost = reinterpret_cast<int*>(smem + Lay<M>::kOffCost);  // wavefront cost of each candidate pitch
     if (tid < kPitchCands) s_cost[tid] = 0;
     const int tx = blockIdx.x % tp.tiles_x, ty = blockIdx.x / tp.tiles_x;
     const int x0 = tx * kTileW, y0 = ty * M::kTileH;
@@ -703,7 +723,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     dr.ext[0] = dr.ext[1] = dr.ext[2] = dr.ext[3] = 0.0;
     int nan_px = 0;
     if (dynr) {  // tile extremes of the normalised coordinates (frame independent)
-        double* s_ext = reinterpret_cast<double*>(smem + kOffExt);
+        double* s_ext = reinterpret_cast<double*>(smem + Lay<M>::kOffExt);
         double e0 = CUDART_INF, e1 = -CUDART_INF, e2 = CUDART_INF, e3 = -CUDART_INF;
         if (sampler) {
 #pragma unroll
@@ -745,11 +765,18 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     const int wbytes = bx1 - bx0, nrows = mxy + M::kHi + 1 - ry0;
     // Taps outside the source read TMA's zero fill = BORDER_CONSTANT(0); only unbounded footprints (NaN / huge
     // coordinates saturate to +-32768) and partial edge tiles leave the fast path.
+    // ... and tiles whose item (FR frames x box rows x pitch) does not fit the staging area
+    auto box_rows_of = [](int rows) {
+        return M::kRowsMin + (rows <= M::kRowsMin ? 0 : (rows - M::kRowsMin + kRowsStep - 1) / kRowsStep) * kRowsStep;
+    };
+    auto stage_fits = [&](int rows, int pitch_bytes) {
+        return ((FR * box_rows_of(rows) * pitch_bytes + 127) & ~127) <= Lay<M>::kStageArea;
+    };
     bool fast = full_tile && wbytes <= kPitchMax && nrows <= M::kRowsMin + (kRowSizes - 1) * kRowsStep &&
-                mnx > -32768 && mny > -32768 && mxx < 32767 && mxy < 32767;
+                mnx > -32768 && mny > -32768 && mxx < 32767 && mxy < 32767 && stage_fits(nrows, max(wbytes, kPitchMin));
     int dyn_wbytes = 0, dyn_nrows = 0;
     if (dynr) {
-        const double* s_ext = reinterpret_cast<const double*>(smem + kOffExt);
+        const double* s_ext = reinterpret_cast<const double*>(smem + Lay<M>::kOffExt);
         dr.ext[0] = dr.ext[2] = CUDART_INF;
         dr.ext[1] = dr.ext[3] = -CUDART_INF;
 #pragma unroll
@@ -781,7 +808,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         dyn_nrows = __reduce_max_sync(0xffffffffu, dyn_nrows);
         ok = __all_sync(0xffffffffu, ok);
         fast = full_tile && ok && !nan_px && dyn_wbytes <= kPitchMax &&
-               dyn_nrows <= M::kRowsMin + (kRowSizes - 1) * kRowsStep;
+               dyn_nrows <= M::kRowsMin + (kRowSizes - 1) * kRowsStep && stage_fits(dyn_nrows, max(dyn_wbytes, kPitchMin));
     }
 
     if (!fast) {  // per-pixel gather from global memory with full border handling (rare tiles)
@@ -829,7 +856,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     if (tp.debug & 1) pitch = pitch <= 160 ? 160 : (pitch <= 224 ? 224 : 256);
     // (not worth ~100 instructions per thread when the tile serves only a few frames: tightest box then)
     if (!dynr && (f1 - f0) * nv >= 8) {
-        const int box_rows = M::kRowsMin + (nrows <= M::kRowsMin ? 0 : (nrows - M::kRowsMin + kRowsStep - 1) / kRowsStep) * kRowsStep;
+        const int box_rows = box_rows_of(nrows);
         if (sampler) {
             const int row = (sy[0] >> kInterBits) - M::kLo - ry0, col = 3 * ((sx[0] >> kInterBits) - M::kLo) - bx0;
             int cost = 0;
@@ -854,7 +881,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         for (int e = 0; e < kPitchCands; ++e) {
             const int pe = pitch + kPitchStep * e;
             const int c = s_cost[e] + box_rows * pe / 64;
-            if (pe <= kPitchMax && c < best_cost) { best_cost = c; best = e; }
+            if (pe <= kPitchMax && stage_fits(nrows, pe) && c < best_cost) { best_cost = c; best = e; }
         }
         if (!(tp.debug & 1)) pitch += kPitchStep * best;
     }
@@ -868,6 +895,17 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         pc[k].boff = off & ~3;
         pc[k].sh = (off & 3) * 8;
         if (sampler && !dynr) M::weights(pc[k], sx[k] & 31, sy[k] & 31, tp.tab);
+    }
+    if constexpr (M::kWeightSmem != 0) {
+        // fixed radius: the pixel's weights do not change from frame to frame -> private copy in shared memory
+        // (written and read by this thread only: no barrier)
+        if (!dynr && sampler) {
+            uint8_t* slot = smem + Lay<M>::kOffW + tid * 16;
+#pragma unroll
+            for (int ky = 0; ky < 8; ++ky)
+                *reinterpret_cast<uint4*>(slot + ky * (kSamplers * 16)) = __ldg(reinterpret_cast<const uint4*>(pc[0].w) + ky);
+            pc[0].ws = smem_u32(slot);
+        }
     }
     TileGeom tg;
     tg.nrows = dynr ? dyn_nrows : nrows;
@@ -1028,7 +1066,7 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
     int dev = 0;
     VR180_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !attr_done[dev].load(std::memory_order_acquire)) {
-        VR180_CUDA(cudaFuncSetAttribute(k_warp_tiled<M, DYN, FR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        VR180_CUDA(cudaFuncSetAttribute(k_warp_tiled<M, DYN, FR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<M>::kSmemBytes));
         attr_done[dev].store(1, std::memory_order_release);
     }
 
@@ -1057,7 +1095,7 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
         match_std_chain(c, tp.std[a.view[g].chain_idx ? 1 : 0]);
     }
     dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)n_groups, (unsigned)chunks);
-    k_warp_tiled<M, DYN, FR><<<grid, kThreads, kSmemBytes, st>>>(a, c0, c1, tp, tm);
+    k_warp_tiled<M, DYN, FR><<<grid, kThreads, Lay<M>::kSmemBytes, st>>>(a, c0, c1, tp, tm);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     VR180_CUDA(cudaGetLastError());
     return VR180_OK;
