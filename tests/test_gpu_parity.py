@@ -409,6 +409,27 @@ def test_tiled_per_frame_radius_equal_radii_take_fixed_pipeline(interp):
         assert np.array_equal(got[f], ref), (interp, f)
 
 
+@pytest.mark.parametrize("interp", [1, 2, 4])
+def test_tiled_long_batch_many_ring_wraps(interp):
+    """131 frames (odd: two-frame items end with a phantom frame) through one launch: the stage ring, the out-buffer
+    ring and every mbarrier phase wrap dozens of times.  Every frame is checked against cv2.remap on the oracle's maps."""
+    import torch
+
+    n, hin, win, wout, hout = 131, 96, 128, 96, 64
+    q = V.from_rotation_vector([0.02, 0.03, -0.04])
+    t = V.EquirectangularEncoder() * V.Euclidean3DRotator(q) * V.FisheyeDecoder("equidistant")
+    rng = np.random.default_rng(17)
+    ln = rng.integers(0, 256, (n, hin, win, 3), dtype=np.uint8)
+    rn = rng.integers(0, 256, (n, hin, win, 3), dtype=np.uint8)
+    got = V.SbsWarper(t, size_input=(hin, win), size_output=(wout, hout), interpolation=interp, radius=48.0)(
+        torch.from_numpy(ln).cuda(), torch.from_numpy(rn).cuda()).cpu().numpy()
+    ops = [("equirect_enc", True), ("rot3", chain_np.quat_to_matrix(*q.components).ravel().tolist()), ("fisheye_dec", "equidistant")]
+    xm, ym = chain_np.get_map(ops, radius=48.0, size_input=(hin, win), size_output=(wout, hout))
+    for f in range(n):
+        want = np.concatenate([cv2.remap(ln[f], xm, ym, interpolation=interp), cv2.remap(rn[f], xm, ym, interpolation=interp)], axis=1)
+        assert np.array_equal(got[f], want), (interp, f)
+
+
 def test_tiled_sbs_offset_not_16_byte_aligned_takes_generic_kernel():
     """TMA boxes must start at 16-byte aligned global addresses: an output width whose eye offset (W * 3 bytes) is
     not a multiple of 16 is not eligible for the tiled kernel and must still be exact through the generic one."""
