@@ -307,7 +307,7 @@ def test_sbs_warper_per_eye_tuple_and_auto_radius():
         assert np.array_equal(got[f], want), f
 
 
-@pytest.mark.parametrize("interp", [1, 2, 4])
+@pytest.mark.parametrize("interp", [0, 1, 2, 4])
 @pytest.mark.parametrize("per_eye", [False, True])
 def test_tiled_pipeline_ring_wraparound_and_source_edges(interp, per_eye):
     """Stress of the tiled TMA pipeline (csrc/tiled.cu): an odd, long batch (stage ring, out-buffer ring and
@@ -343,7 +343,7 @@ def test_tiled_pipeline_ring_wraparound_and_source_edges(interp, per_eye):
         assert np.array_equal(got[f], want), (interp, per_eye, f, int((got[f] != want).sum()))
 
 
-@pytest.mark.parametrize("interp", [1, 2, 4])
+@pytest.mark.parametrize("interp", [0, 1, 2, 4])
 @pytest.mark.parametrize("per_eye", [False, True])
 def test_tiled_per_frame_radius_on_device(interp, per_eye):
     """Per-frame radius consumed on the device by the tiled kernel (vr180_mapsrc_t::radius_dev): every frame has
@@ -381,7 +381,7 @@ def test_tiled_per_frame_radius_on_device(interp, per_eye):
         assert np.array_equal(got[f], want), (interp, per_eye, f, r, int((got[f] != want).sum()))
 
 
-@pytest.mark.parametrize("interp", [1, 2, 4])
+@pytest.mark.parametrize("interp", [0, 1, 2, 4])
 def test_tiled_per_frame_radius_equal_radii_take_fixed_pipeline(interp):
     """A chunk whose frames all carry the same device radius (a static rig) is routed to the fixed-radius pipeline
     inside the per-frame-radius kernel (csrc/tiled.cu, `dynr`): the result must be the fixed-radius result, bit for
@@ -409,7 +409,7 @@ def test_tiled_per_frame_radius_equal_radii_take_fixed_pipeline(interp):
         assert np.array_equal(got[f], ref), (interp, f)
 
 
-@pytest.mark.parametrize("interp", [1, 2, 4])
+@pytest.mark.parametrize("interp", [0, 1, 2, 4])
 def test_tiled_long_batch_many_ring_wraps(interp):
     """131 frames (odd: two-frame items end with a phantom frame) through one launch: the stage ring, the out-buffer
     ring and every mbarrier phase wrap dozens of times.  Every frame is checked against cv2.remap on the oracle's maps."""

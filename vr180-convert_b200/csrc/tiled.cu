@@ -197,6 +197,8 @@ __device__ __forceinline__ uint32_t dp2a_hi_su(uint32_t w, uint32_t px, uint32_t
 // it), the per-pixel constants and the sampling of one pixel from the staged rectangle.
 struct Linear {
     static constexpr int kPx = 4, kTileH = 32, kLo = 0, kHi = 1, kRowsMin = 32, kInterp = VR180_INTER_LINEAR;
+    static constexpr int kShift = kInterBits;  // coordinates are 1/32-pixel fixed point: sx = cvRound(x * 32)
+    __device__ static __forceinline__ int quant(float m) { return quantise(m); }
     static constexpr int kStageArea = kStageAreaDefault, kWeightSmem = 0;
     static constexpr bool kRowPatch = true;  // a warp step = 32 pixels of one output row (pixel k of a thread: row 4 band + k)
     struct Pixel {  // constant over the frames of the batch
@@ -231,8 +233,29 @@ struct Linear {
     }
 };
 
+// INTER_NEAREST: ix = saturate_int16(cvRound(x)) (no sub-pixel grid), out = src[iy, ix].
+struct Nearest {
+    static constexpr int kPx = 4, kTileH = 32, kLo = 0, kHi = 0, kRowsMin = 32, kInterp = VR180_INTER_NEAREST;
+    static constexpr int kShift = 0;
+    __device__ static __forceinline__ int quant(float m) { return cv_round(m); }
+    static constexpr int kStageArea = kStageAreaDefault, kWeightSmem = 0;
+    static constexpr bool kRowPatch = true;
+    struct Pixel {
+        int boff;  // byte offset (4-aligned) of the 8-byte window that holds the pixel
+        int sh;    // 8 * (byte offset & 3)
+    };
+    __device__ static __forceinline__ void weights(Pixel&, int, int, const short*) {}
+    __device__ static __forceinline__ uint32_t sample(uint32_t sbuf, const Pixel& p, uint32_t) {
+        uint32_t a0, a1;
+        asm volatile("ld.shared.u32 %0, [%2];\n\tld.shared.u32 %1, [%2+4];" : "=r"(a0), "=r"(a1) : "r"(sbuf + (uint32_t)p.boff));
+        return __funnelshift_r(a0, a1, p.sh);  // [c0 c1 c2 .]: the re-pack never looks at byte 3
+    }
+};
+
 struct Cubic {
     static constexpr int kPx = 2, kTileH = 16, kLo = 1, kHi = 2, kRowsMin = 16, kInterp = VR180_INTER_CUBIC;
+    static constexpr int kShift = kInterBits;  // coordinates are 1/32-pixel fixed point: sx = cvRound(x * 32)
+    __device__ static __forceinline__ int quant(float m) { return quantise(m); }
     static constexpr int kStageArea = kStageAreaDefault, kWeightSmem = 0;
     static constexpr bool kRowPatch = false;  // a warp step = an 8 x 4 pixel patch (pixel k of a thread: column + 8 k)
     struct Pixel {
@@ -280,6 +303,8 @@ struct Cubic {
 // and ~120 shared-memory wavefronts per pixel step.
 struct Lanczos4 {
     static constexpr int kPx = 1, kTileH = 8, kLo = 3, kHi = 4, kRowsMin = 16, kInterp = VR180_INTER_LANCZOS4;
+    static constexpr int kShift = kInterBits;  // coordinates are 1/32-pixel fixed point: sx = cvRound(x * 32)
+    __device__ static __forceinline__ int quant(float m) { return quantise(m); }
     static constexpr int kStageArea = 16384, kWeightSmem = kSamplers * 128;  // 16 KB of stages + 32 KB of weights
     static constexpr bool kRowPatch = false;
     struct Pixel {
@@ -339,12 +364,14 @@ struct DynRadius {
     double cx, cy;         // centre of the final DenormalizeTransformer
     double ext[4];         // tile extremes: nx min, nx max, ny min, ny max
 };
-__device__ __forceinline__ int denorm_q(double n, double rad, double c) {  // astype(float32), cvRound(x * 32)
-    return quantise(__double2float_rn(add_rn(mul_rn(n, rad), c)));
+template <class M>
+__device__ __forceinline__ int denorm_q(double n, double rad, double c) {  // astype(float32), the mode's cvRound
+    return M::quant(__double2float_rn(add_rn(mul_rn(n, rad), c)));
 }
 // integer pixel range [lo, hi] of the taps' base coordinate over the tile for one frame
+template <class M>
 __device__ __forceinline__ void dyn_range(double nmin, double nmax, double rad, double c, int& lo, int& hi) {
-    const int a = sat16(denorm_q(nmin, rad, c) >> kInterBits), b = sat16(denorm_q(nmax, rad, c) >> kInterBits);
+    const int a = sat16(denorm_q<M>(nmin, rad, c) >> M::kShift), b = sat16(denorm_q<M>(nmax, rad, c) >> M::kShift);
     lo = min(a, b);
     hi = max(a, b);
 }
@@ -412,9 +439,9 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
                 const double rad = __ldg(dr.radius + f);
                 if (rad == rad) {
                     int lo, hi;
-                    dyn_range(dr.ext[0], dr.ext[1], rad, dr.cx, lo, hi);
+                    dyn_range<M>(dr.ext[0], dr.ext[1], rad, dr.cx, lo, hi);
                     bx0 = (3 * (lo - M::kLo)) & ~15;
-                    dyn_range(dr.ext[2], dr.ext[3], rad, dr.cy, lo, hi);
+                    dyn_range<M>(dr.ext[2], dr.ext[3], rad, dr.cy, lo, hi);
                     ry0 = lo - M::kLo;
                 } else {  // get_radius found no transition: every coordinate is NaN -> border colour
                     bx0 = ry0 = -(1 << 20);
@@ -482,8 +509,8 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
                 cur_have = rad == rad;
 #pragma unroll
                 for (int k = 0; k < M::kPx; ++k) {
-                    const int qx = denorm_q(nx[k], rad, dr.cx), qy = denorm_q(ny[k], rad, dr.cy);
-                    const int off = ((qy >> kInterBits) - M::kLo - org.y) * pitch + 3 * ((qx >> kInterBits) - M::kLo) - org.x;
+                    const int qx = denorm_q<M>(nx[k], rad, dr.cx), qy = denorm_q<M>(ny[k], rad, dr.cy);
+                    const int off = ((qy >> M::kShift) - M::kLo - org.y) * pitch + 3 * ((qx >> M::kShift) - M::kLo) - org.x;
                     cur[k].boff = cur_have ? (off & ~3) : 0;
                     cur[k].sh = (off & 3) * 8;
                     M::weights(cur[k], qx & 31, qy & 31, tab);
@@ -626,8 +653,8 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                             ny[k] = s.y;
                         } else {
                             op_denormalize(c.den, s);
-                            sx[k] = quantise(__double2float_rn(s.x));  // astype(float32) then cvRound(x * 32)
-                            sy[k] = quantise(__double2float_rn(s.y));
+                            sx[k] = M::quant(__double2float_rn(s.x));  // astype(float32) then cvRound(x * 32)
+                            sy[k] = M::quant(__double2float_rn(s.y));
                         }
                     }
                 };
@@ -640,7 +667,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                     seed(k, s);
                     run_ops(ch, 2, ch.n_ops - (dyn ? 1 : 0), s);
                     to_xy(s);
-                    const int qx = quantise(__double2float_rn(s.x)), qy = quantise(__double2float_rn(s.y));
+                    const int qx = M::quant(__double2float_rn(s.x)), qy = M::quant(__double2float_rn(s.y));
 #pragma unroll
                     for (int kk = 0; kk < kPx; ++kk)
                         if (kk == k) { sx[kk] = qx; sy[kk] = qy; nx[kk] = s.x; ny[kk] = s.y; }
@@ -652,7 +679,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                 double xs, ys;
                 if (dyn) eval_chain_normalised(ch, x0 + pcol(k), y0 + prow(k), xs, ys);
                 else eval_chain(ch, x0 + pcol(k), y0 + prow(k), xs, ys);
-                const int qx = quantise(__double2float_rn(xs)), qy = quantise(__double2float_rn(ys));
+                const int qx = M::quant(__double2float_rn(xs)), qy = M::quant(__double2float_rn(ys));
 #pragma unroll
                 for (int kk = 0; kk < kPx; ++kk)
                     if (kk == k) { sx[kk] = qx; sy[kk] = qy; nx[kk] = xs; ny[kk] = ys; }
@@ -665,8 +692,8 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
             sx[k] = sy[k] = (int)0x80000000;
             if (i < a.W && j < a.H) {
                 if (mv.map_kind == VR180_MAPSRC_FLOAT2) {
-                    sx[k] = quantise(__ldg(mv.xmap + (long long)j * mv.map_pitch + i));
-                    sy[k] = quantise(__ldg(mv.ymap + (long long)j * mv.map_pitch + i));
+                    sx[k] = M::quant(__ldg(mv.xmap + (long long)j * mv.map_pitch + i));
+                    sy[k] = M::quant(__ldg(mv.ymap + (long long)j * mv.map_pitch + i));
                 } else {
                     const int2 q = __ldg(mv.fixed + (long long)j * mv.map_pitch + i);
                     sx[k] = q.x;
@@ -691,8 +718,8 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
             const double cx = ch.ops[ch.n_ops - 1].p[2], cy = ch.ops[ch.n_ops - 1].p[3];
 #pragma unroll
             for (int k = 0; k < kPx; ++k) {
-                sx[k] = denorm_q(nx[k], r0, cx);
-                sy[k] = denorm_q(ny[k], r0, cy);
+                sx[k] = denorm_q<M>(nx[k], r0, cx);
+                sy[k] = denorm_q<M>(ny[k], r0, cy);
             }
         }
     }
@@ -701,7 +728,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
 #pragma unroll
     for (int k = 0; k < kPx; ++k) {
-        const int ix = sat16(sx[k] >> kInterBits), iy = sat16(sy[k] >> kInterBits);
+        const int ix = sat16(sx[k] >> M::kShift), iy = sat16(sy[k] >> M::kShift);
         mnx = min(mnx, ix);
         mxx = max(mxx, ix);
         mny = min(mny, iy);
@@ -796,10 +823,10 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
             const double rad = __ldg(dr.radius + f);
             if (rad == rad) {
                 int lo, hi;
-                dyn_range(dr.ext[0], dr.ext[1], rad, dr.cx, lo, hi);
+                dyn_range<M>(dr.ext[0], dr.ext[1], rad, dr.cx, lo, hi);
                 ok &= (lo > -32768) & (hi < 32767);
                 dyn_wbytes = max(dyn_wbytes, ((3 * (hi + M::kHi + 1) + 15) & ~15) - ((3 * (lo - M::kLo)) & ~15));
-                dyn_range(dr.ext[2], dr.ext[3], rad, dr.cy, lo, hi);
+                dyn_range<M>(dr.ext[2], dr.ext[3], rad, dr.cy, lo, hi);
                 ok &= (lo > -32768) & (hi < 32767);
                 dyn_nrows = max(dyn_nrows, hi + M::kHi + 1 - (lo - M::kLo));
             }
@@ -822,14 +849,16 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                         int qx = sx[k], qy = sy[k];
                         if (dynr) {
                             const double rad = __ldg(dr.radius + f);
-                            qx = denorm_q(nx[k], rad, dr.cx);
-                            qy = denorm_q(ny[k], rad, dr.cy);
+                            qx = denorm_q<M>(nx[k], rad, dr.cx);
+                            qy = denorm_q<M>(ny[k], rad, dr.cy);
                         }
                         for (int v = v_begin; v < v_end; ++v) {
                             const ViewArgs& vw = a.view[v];
                             Src s{vw.src + (long long)f * vw.frame_stride, vw.rows, vw.cols, vw.pitch};
                             int px[3];
-                            if (M::kInterp == VR180_INTER_LINEAR)
+                            if (M::kInterp == VR180_INTER_NEAREST)
+                                fetch_tap<3>(s, sat16(qx), sat16(qy), VR180_BORDER_CONSTANT, a.bv, px);
+                            else if (M::kInterp == VR180_INTER_LINEAR)
                                 sample_linear<3>(s, qx, qy, VR180_BORDER_CONSTANT, a.bv, px);
                             else if (M::kInterp == VR180_INTER_CUBIC)
                                 sample_tab<3, 4>(s, qx, qy, tp.tab, VR180_BORDER_CONSTANT, a.bv, px);
@@ -858,7 +887,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     if (!dynr && (f1 - f0) * nv >= 8) {
         const int box_rows = box_rows_of(nrows);
         if (sampler) {
-            const int row = (sy[0] >> kInterBits) - M::kLo - ry0, col = 3 * ((sx[0] >> kInterBits) - M::kLo) - bx0;
+            const int row = (sy[0] >> M::kShift) - M::kLo - ry0, col = 3 * ((sx[0] >> M::kShift) - M::kLo) - bx0;
             int cost = 0;
 #pragma unroll
             for (int e = 0; e < kPitchCands; ++e) {
@@ -872,7 +901,8 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                 if (lane == e) cost = deg;
             }
             constexpr int kStepsPerWarp = M::kTileH * kTileW / kSamplers;  // warp steps (32 pixels) of a tile, per warp
-            constexpr int kLoadsPerTile = kStepsPerWarp * (M::kInterp == VR180_INTER_LINEAR ? 6 : M::kInterp == VR180_INTER_CUBIC ? 16 : 56);
+            constexpr int kLoadsPerTile = kStepsPerWarp * (M::kInterp == VR180_INTER_NEAREST ? 2 : M::kInterp == VR180_INTER_LINEAR ? 6
+                                                           : M::kInterp == VR180_INTER_CUBIC ? 16 : 56);
             if (lane < kPitchCands) atomicAdd(&s_cost[lane], cost * kLoadsPerTile);
         }
         __syncthreads();
@@ -890,7 +920,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     typename M::Pixel pc[kPx];
 #pragma unroll
     for (int k = 0; k < kPx; ++k) {
-        const int ix = sx[k] >> kInterBits, iy = sy[k] >> kInterBits;
+        const int ix = sx[k] >> M::kShift, iy = sy[k] >> M::kShift;
         const int off = (iy - M::kLo - ry0) * pitch + 3 * (ix - M::kLo) - bx0;
         pc[k].boff = off & ~3;
         pc[k].sh = (off & 3) * 8;
@@ -1108,8 +1138,12 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
                        const short* tab_cubic, cudaStream_t st) {
     // `tab_cubic`: the weight table of the requested interpolation (1024 x 16 bicubic or 1024 x 64 Lanczos4)
     if (channels != 3 || a0.border_mode != VR180_BORDER_CONSTANT) return VR180_ERR_UNSUPPORTED;
-    if (interp != VR180_INTER_LINEAR && interp != VR180_INTER_CUBIC && interp != VR180_INTER_LANCZOS4)
+    if (interp != VR180_INTER_NEAREST && interp != VR180_INTER_LINEAR && interp != VR180_INTER_CUBIC &&
+        interp != VR180_INTER_LANCZOS4)
         return VR180_ERR_UNSUPPORTED;
+    if (interp == VR180_INTER_NEAREST)  // the fixed-point LUT is a 1/32-pixel grid; NEAREST rounds the float coordinate itself
+        for (int v = 0; v < a0.n_views; ++v)
+            if (a0.view[v].map_kind == VR180_MAPSRC_FIXED) return VR180_ERR_UNSUPPORTED;
     if (a0.bv[0] | a0.bv[1] | a0.bv[2]) return VR180_ERR_UNSUPPORTED;  // staged tiles assume a zero border colour
     const int n_groups = a0.share_map ? 1 : a0.n_views;
     for (int v = 0; v < a0.n_views; ++v) {
@@ -1133,11 +1167,16 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
     if (n_dyn != 0 && n_dyn != n_groups) return VR180_ERR_UNSUPPORTED;
     const bool dyn = n_dyn != 0;
     // two frames per pipeline item when the frames share their rectangles and every CTA gets at least two of them
-    const int tile_h = interp == VR180_INTER_LINEAR  ? tiled::Linear::kTileH
+    const int tile_h = interp == VR180_INTER_LINEAR || interp == VR180_INTER_NEAREST ? tiled::Linear::kTileH
                        : interp == VR180_INTER_CUBIC ? tiled::Cubic::kTileH
                                                      : tiled::Lanczos4::kTileH;
     const long long tiles = (long long)((a0.W + tiled::kTileW - 1) / tiled::kTileW) * ((a0.H + tile_h - 1) / tile_h) * n_groups;
     const bool pairs = !dyn && frames_per_cta(tiles, a0.n_frames) >= 2;
+    if (interp == VR180_INTER_NEAREST) {
+        if (dyn) return launch_mode<tiled::Nearest, true, 1>(a0, c0, c1, nullptr, st);
+        return pairs ? launch_mode<tiled::Nearest, false, 2>(a0, c0, c1, nullptr, st)
+                     : launch_mode<tiled::Nearest, false, 1>(a0, c0, c1, nullptr, st);
+    }
     if (interp == VR180_INTER_LINEAR) {
         if (dyn) return launch_mode<tiled::Linear, true, 1>(a0, c0, c1, nullptr, st);
         return pairs ? launch_mode<tiled::Linear, false, 2>(a0, c0, c1, nullptr, st)
