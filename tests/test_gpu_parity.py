@@ -430,6 +430,30 @@ def test_tiled_long_batch_many_ring_wraps(interp):
         assert np.array_equal(got[f], want), (interp, f)
 
 
+@pytest.mark.parametrize("interp", [1, 2])
+def test_tiled_multi_frame_items_with_phantom_frames(interp):
+    """Enough tiles (1024 x 512 output) for the launcher to keep >= 8 frames per CTA: bicubic then packs FOUR frames
+    per pipeline item, bilinear two.  22 frames -> chunks of 12 and 10 frames: the last item of the launch has two
+    phantom frames past the end of the batch (TMA zero-fills their loads and drops their stores)."""
+    import torch
+
+    n, hin, win, wout, hout = 22, 320, 320, 1024, 512
+    t = V.EquirectangularEncoder() * V.PolynomialScaler([0, 1, 0.03]) * V.FisheyeDecoder("equidistant")
+    rng = np.random.default_rng(23)
+    ln = rng.integers(0, 256, (n, hin, win, 3), dtype=np.uint8)
+    rn = rng.integers(0, 256, (n, hin, win, 3), dtype=np.uint8)
+    out = torch.full((n + 1, hout, 2 * wout, 3), 77, dtype=torch.uint8, device="cuda")  # one guard frame behind the batch
+    V.SbsWarper(t, size_input=(hin, win), size_output=(wout, hout), interpolation=interp, radius=160.0)(
+        torch.from_numpy(ln).cuda(), torch.from_numpy(rn).cuda(), out=out[:n])
+    got = out.cpu().numpy()
+    assert (got[n] == 77).all(), "a phantom frame was stored behind the batch"
+    xm, ym = chain_np.get_map([("equirect_enc", True), ("poly", [0, 1, 0.03]), ("fisheye_dec", "equidistant")], radius=160.0,
+                              size_input=(hin, win), size_output=(wout, hout))
+    for f in range(n):
+        want = np.concatenate([cv2.remap(ln[f], xm, ym, interpolation=interp), cv2.remap(rn[f], xm, ym, interpolation=interp)], axis=1)
+        assert np.array_equal(got[f], want), (interp, f)
+
+
 def test_tiled_sbs_offset_not_16_byte_aligned_takes_generic_kernel():
     """TMA boxes must start at 16-byte aligned global addresses: an output width whose eye offset (W * 3 bytes) is
     not a multiple of 16 is not eligible for the tiled kernel and must still be exact through the generic one."""

@@ -70,12 +70,12 @@ constexpr int kPitchMin = 96, kPitchMax = 256, kPitchStep = 16;
 constexpr int kWidths = (kPitchMax - kPitchMin) / kPitchStep + 1;  // 11 box widths
 constexpr int kPitchCands = 4;
 constexpr int kStageAreaDefault = 40960;  // >= 1 two-frame stage of the largest admissible rectangle (64 rows x 256 B)
-constexpr int kOutBufs = 4;        // power of two
+constexpr int kOutBufs = 4;        // ofull / oempty barrier slots; out buffers in use: M::kOutTiles / FR (a power of two <= 4)
 // Shared-memory layout of a CTA; the staging area is a property of the interpolation mode (M::kStageArea).
 template <class M>
 struct Lay {
     static constexpr int kStageArea = M::kStageArea;
-    static constexpr int kOutArea = kOutBufs * M::kTileH * kTileW * 3;
+    static constexpr int kOutArea = M::kOutTiles * M::kTileH * kTileW * 3;
     static constexpr int kOffOut = kStageArea;
     static constexpr int kOffTrig = kOffOut + kOutArea;
     static constexpr int kOffRed = kOffTrig + 4 * 32 * 8;
@@ -199,7 +199,7 @@ struct Linear {
     static constexpr int kPx = 4, kTileH = 32, kLo = 0, kHi = 1, kRowsMin = 32, kInterp = VR180_INTER_LINEAR;
     static constexpr int kShift = kInterBits;  // coordinates are 1/32-pixel fixed point: sx = cvRound(x * 32)
     __device__ static __forceinline__ int quant(float m) { return quantise(m); }
-    static constexpr int kStageArea = kStageAreaDefault, kWeightSmem = 0;
+    static constexpr int kStageArea = kStageAreaDefault, kWeightSmem = 0, kOutTiles = 4, kMaxFR = 2;
     static constexpr bool kRowPatch = true;  // a warp step = 32 pixels of one output row (pixel k of a thread: row 4 band + k)
     struct Pixel {  // constant over the frames of the batch
         int boff;          // byte offset (4-aligned) of the 12-byte tap window of row 0 inside a stage buffer
@@ -238,7 +238,7 @@ struct Nearest {
     static constexpr int kPx = 4, kTileH = 32, kLo = 0, kHi = 0, kRowsMin = 32, kInterp = VR180_INTER_NEAREST;
     static constexpr int kShift = 0;
     __device__ static __forceinline__ int quant(float m) { return cv_round(m); }
-    static constexpr int kStageArea = kStageAreaDefault, kWeightSmem = 0;
+    static constexpr int kStageArea = kStageAreaDefault, kWeightSmem = 0, kOutTiles = 4, kMaxFR = 2;
     static constexpr bool kRowPatch = true;
     struct Pixel {
         int boff;  // byte offset (4-aligned) of the 8-byte window that holds the pixel
@@ -256,7 +256,9 @@ struct Cubic {
     static constexpr int kPx = 2, kTileH = 16, kLo = 1, kHi = 2, kRowsMin = 16, kInterp = VR180_INTER_CUBIC;
     static constexpr int kShift = kInterBits;  // coordinates are 1/32-pixel fixed point: sx = cvRound(x * 32)
     __device__ static __forceinline__ int quant(float m) { return quantise(m); }
-    static constexpr int kStageArea = kStageAreaDefault, kWeightSmem = 0;
+    // a thread owns only 2 pixels (their 16 table weights take 16 registers), so an item is FOUR frames: the
+    // per-item bookkeeping is paid once per 8 pixels of a thread, as for the bilinear mode
+    static constexpr int kStageArea = kStageAreaDefault, kWeightSmem = 0, kOutTiles = 8, kMaxFR = 4;
     static constexpr bool kRowPatch = false;  // a warp step = an 8 x 4 pixel patch (pixel k of a thread: column + 8 k)
     struct Pixel {
         int boff;       // byte offset (4-aligned) of the 16-byte window of tap row 0 (iy - 1), first tap ix - 1
@@ -306,6 +308,7 @@ struct Lanczos4 {
     static constexpr int kShift = kInterBits;  // coordinates are 1/32-pixel fixed point: sx = cvRound(x * 32)
     __device__ static __forceinline__ int quant(float m) { return quantise(m); }
     static constexpr int kStageArea = 16384, kWeightSmem = kSamplers * 128;  // 16 KB of stages + 32 KB of weights
+    static constexpr int kOutTiles = 4, kMaxFR = 2;
     static constexpr bool kRowPatch = false;
     struct Pixel {
         int boff;        // byte offset (4-aligned) of the 28-byte window of tap row 0 (iy - 3), first tap ix - 3
@@ -407,10 +410,11 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
                                            const typename M::Pixel (&pc)[M::kPx], const TileGeom& tg, const int pitch,
                                            uint8_t* smem, int band, int cg, const DynRadius& dr,
                                            const double (&nx)[M::kPx], const double (&ny)[M::kPx], const short* tab) {
-    static_assert(FR == 1 || (FR == 2 && !DYN), "a per-frame radius gives every frame its own rectangle");
+    static_assert(FR == 1 || !DYN, "a per-frame radius gives every frame its own rectangle");
+    static_assert(M::kOutTiles / FR >= 2, "at least two out buffers of one item each");
     constexpr int kOutTileBytes = M::kTileH * kTileW * 3;
     constexpr int kOutItemBytes = FR * kOutTileBytes;
-    constexpr int OB = kOutBufs / FR;  // out buffers of one item each (the same area either way)
+    constexpr int OB = M::kOutTiles / FR < kOutBufs ? M::kOutTiles / FR : kOutBufs;  // out buffers of one item each
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s_stage = smem_u32(smem), s_full = s_stage + Lay<M>::kOffBar;
     const uint32_t s_ofull = s_full + 2 * kMaxStages * 8, s_oempty = s_ofull + kOutBufs * 8, s_out = s_stage + Lay<M>::kOffOut;
@@ -1110,7 +1114,7 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
     tp.debug = debug;
     const long long tiles = (long long)tiles_x * tiles_y * n_groups;
     int fpc = frames_per_cta(tiles, a.n_frames);
-    if (FR == 2 && (fpc & 1)) ++fpc;  // chunks start at even frames: a phantom frame can only lie past the batch
+    fpc = (fpc + FR - 1) / FR * FR;  // chunks start at multiples of FR: phantom frames can only lie past the batch
     a.frames_per_cta = fpc;
     const int chunks = (a.n_frames + fpc - 1) / fpc;
     if (chunks > 65535 || tiles_x * (long long)tiles_y > 0x7fffffffLL) return VR180_ERR_UNSUPPORTED;
@@ -1189,6 +1193,7 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
                      : launch_mode<tiled::Lanczos4, false, 1>(a0, c0, c1, tab_cubic, st);
     }
     if (dyn) return launch_mode<tiled::Cubic, true, 1>(a0, c0, c1, tab_cubic, st);
+    if (frames_per_cta(tiles, a0.n_frames) >= 8) return launch_mode<tiled::Cubic, false, 4>(a0, c0, c1, tab_cubic, st);
     return pairs ? launch_mode<tiled::Cubic, false, 2>(a0, c0, c1, tab_cubic, st)
                  : launch_mode<tiled::Cubic, false, 1>(a0, c0, c1, tab_cubic, st);
 }
