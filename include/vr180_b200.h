@@ -189,8 +189,9 @@ int vr180_pack_lut(const float* xmap_dev, const float* ymap_dev, int64_t map_pit
  * (2b) remap / fused warp + SBS packing -- replaces cv.remap per image (remapper.py:388-398) and
  *      np.concatenate(axis=1) (remapper.py:518): each view is written straight into its column range of the
  *      destination frame.  uint8, 1/3/4 channels.  Bit-exact to cv2.remap for the same float32 maps.
- *      Performance note (results are identical either way): the TMA-tiled kernel serves 3 channels, LINEAR or
- *      CUBIC, BORDER_CONSTANT with a zero border value, when every base pointer, row pitch and frame stride is a
+ *      Performance note (results are identical either way): the TMA-tiled kernel serves 3 channels, NEAREST /
+ *      LINEAR / CUBIC / LANCZOS4, BORDER_CONSTANT with a zero border value (NEAREST not with a MAPSRC_FIXED
+ *      LUT, which stores x * 32), when every base pointer, row pitch and frame stride is a
  *      multiple of 16 bytes and every view's dst_x_offset * 3 is too (a TMA box must start at a 16-byte aligned
  *      global address); any other request runs in the generic per-pixel kernel.
  * ---------------------------------------------------------------------------------------------------- */
