@@ -259,7 +259,7 @@ struct Cubic {
     // a thread owns only 2 pixels (their 16 table weights take 16 registers), so an item is FOUR frames: the
     // per-item bookkeeping is paid once per 8 pixels of a thread, as for the bilinear mode
     static constexpr int kStageArea = kStageAreaDefault, kWeightSmem = 0, kOutTiles = 8, kMaxFR = 4;
-    static constexpr bool kRowPatch = false;  // a warp step = an 8 x 4 pixel patch (pixel k of a thread: column + 8 k)
+    static constexpr bool kRowPatch = true;  // a warp step = 32 pixels of one output row (pixel k of a thread: row 2 warp + k)
     struct Pixel {
         int boff;       // byte offset (4-aligned) of the 16-byte window of tap row 0 (iy - 1), first tap ix - 1
         int sh;
@@ -305,11 +305,11 @@ struct Cubic {
 // and ~120 shared-memory wavefronts per pixel step.
 struct Lanczos4 {
     static constexpr int kPx = 1, kTileH = 8, kLo = 3, kHi = 4, kRowsMin = 16, kInterp = VR180_INTER_LANCZOS4;
+    static constexpr bool kRowPatch = true;  // a warp = one output row of the tile
     static constexpr int kShift = kInterBits;  // coordinates are 1/32-pixel fixed point: sx = cvRound(x * 32)
     __device__ static __forceinline__ int quant(float m) { return quantise(m); }
     static constexpr int kStageArea = 16384, kWeightSmem = kSamplers * 128;  // 16 KB of stages + 32 KB of weights
     static constexpr int kOutTiles = 4, kMaxFR = 2;
-    static constexpr bool kRowPatch = false;
     struct Pixel {
         int boff;        // byte offset (4-aligned) of the 28-byte window of tap row 0 (iy - 3), first tap ix - 3
         int sh;
@@ -485,7 +485,8 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     //   row patch: row 4 band + k, word 3 (lane >> 2) + sub
     //   8 x 4 patch: row 4 band + (lane >> 3), byte 24 (kPx cg + k), word 3 ((lane & 7) >> 2) + sub
     constexpr int kOutStep = M::kRowPatch ? kTileW * 3 : 24;
-    uint32_t outp = s_out + (M::kRowPatch ? (4 * band) * (kTileW * 3) + (3 * (lane >> 2) + sub) * 4
+    const int sw = band * (4 / M::kPx) + cg;  // sampling warp index; with row patches it owns rows kPx sw .. kPx sw + kPx - 1
+    uint32_t outp = s_out + (M::kRowPatch ? (M::kPx * sw) * (kTileW * 3) + (3 * (lane >> 2) + sub) * 4
                                           : (4 * band + (lane >> 3)) * (kTileW * 3) + M::kPx * cg * 24 +
                                                 (3 * ((lane & 7) >> 2) + sub) * 4);
     uint32_t flags = (writer ? 1u : 0u) | (lane == 0 ? 2u : 0u);
@@ -591,7 +592,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     const bool sampler = warp < kSamplers / 32;  // the last warp = TMA producer: no pixels of its own
     const int sw = warp & (kSamplers / 32 - 1), band = sw / kWarpsPerBand, cg = sw % kWarpsPerBand;
     // pixel k of this thread (tile-local): 8 x 4 patches: column lx + 8 k, row ly; row patches: column lane, row 4 band + k
-    const int lx = M::kRowPatch ? lane : 8 * kPx * cg + (lane & 7), ly = M::kRowPatch ? 4 * band : 4 * band + (lane >> 3);
+    const int lx = M::kRowPatch ? lane : 8 * kPx * cg + (lane & 7), ly = M::kRowPatch ? kPx * sw : 4 * band + (lane >> 3);
     auto pcol = [&](int k) { return M::kRowPatch ? lx : lx + 8 * k; };
     auto prow = [&](int k) { return M::kRowPatch ? ly + k : ly; };
     const bool full_tile = (x0 + kTileW <= a.W) && (y0 + M::kTileH <= a.H);
