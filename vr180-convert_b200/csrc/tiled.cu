@@ -320,18 +320,17 @@ struct Lanczos4 {
         p.w = tab + (((ay << 5) | ax) << 6);
         p.ws = 0;
     }
-    __device__ static __forceinline__ uint32_t sample(uint32_t sbuf, const Pixel& p, uint32_t pitch) {
-        const uint32_t* r = reinterpret_cast<const uint32_t*>(
-            static_cast<const uint8_t*>(__cvta_shared_to_generic(sbuf)) + p.boff);
+    // NF frames of an item at once: a tap row's weights are loaded once and applied to every frame
+    template <int NF>
+    __device__ static __forceinline__ void sample_frames(uint32_t sbuf, uint32_t frame_bytes, const Pixel& p, uint32_t pitch,
+                                                         uint32_t (&out)[NF]) {
+        const uint8_t* base = static_cast<const uint8_t*>(__cvta_shared_to_generic(sbuf)) + p.boff;
         const int sh = p.sh;
-        uint32_t acc0 = 16384u, acc1 = 16384u, acc2 = 16384u;  // + 1 << 14 before the >> 15
+        uint32_t acc[NF][3];
 #pragma unroll
-        for (int ky = 0; ky < 8; ++ky, r += pitch / 4) {
-            uint32_t x[7], A[6];
+        for (int f = 0; f < NF; ++f) acc[f][0] = acc[f][1] = acc[f][2] = 16384u;  // + 1 << 14 before the >> 15
 #pragma unroll
-            for (int i = 0; i < 7; ++i) x[i] = r[i];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) A[i] = __funnelshift_r(x[i], x[i + 1], sh);  // 24 tap bytes, byte-aligned
+        for (int ky = 0; ky < 8; ++ky) {
             uint4 wv;
             if (p.ws) {
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -342,19 +341,36 @@ struct Lanczos4 {
             }
             const uint32_t wp[4] = {wv.x, wv.y, wv.z, wv.w};  // {kx 0, 1} {2, 3} {4, 5} {6, 7}
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {  // taps 4 g .. 4 g + 3 = the 12 bytes of A[3 g .. 3 g + 2]
-                const uint32_t A0 = A[3 * g], A1 = A[3 * g + 1], A2 = A[3 * g + 2];
-                const uint32_t q0 = __byte_perm(__byte_perm(A0, A1, 0x0630), A2, 0x5210);  // [t0c0 t1c0 t2c0 t3c0]
-                const uint32_t q1 = __byte_perm(__byte_perm(A0, A1, 0x0741), A2, 0x6210);  // [t0c1 t1c1 t2c1 t3c1]
-                const uint32_t q2 = __byte_perm(__byte_perm(A0, A1, 0x0052), A2, 0x7410);  // [t0c2 t1c2 t2c2 t3c2]
-                acc0 = dp2a_hi_su(wp[2 * g + 1], q0, dp2a_lo_su(wp[2 * g], q0, acc0));
-                acc1 = dp2a_hi_su(wp[2 * g + 1], q1, dp2a_lo_su(wp[2 * g], q1, acc1));
-                acc2 = dp2a_hi_su(wp[2 * g + 1], q2, dp2a_lo_su(wp[2 * g], q2, acc2));
+            for (int f = 0; f < NF; ++f) {
+                const uint32_t* r = reinterpret_cast<const uint32_t*>(base + f * frame_bytes + ky * pitch);
+                uint32_t x[7], A[6];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) x[i] = r[i];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) A[i] = __funnelshift_r(x[i], x[i + 1], sh);  // 24 tap bytes, byte-aligned
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {  // taps 4 g .. 4 g + 3 = the 12 bytes of A[3 g .. 3 g + 2]
+                    const uint32_t A0 = A[3 * g], A1 = A[3 * g + 1], A2 = A[3 * g + 2];
+                    const uint32_t q0 = __byte_perm(__byte_perm(A0, A1, 0x0630), A2, 0x5210);  // [t0c0 t1c0 t2c0 t3c0]
+                    const uint32_t q1 = __byte_perm(__byte_perm(A0, A1, 0x0741), A2, 0x6210);  // [t0c1 t1c1 t2c1 t3c1]
+                    const uint32_t q2 = __byte_perm(__byte_perm(A0, A1, 0x0052), A2, 0x7410);  // [t0c2 t1c2 t2c2 t3c2]
+                    acc[f][0] = dp2a_hi_su(wp[2 * g + 1], q0, dp2a_lo_su(wp[2 * g], q0, acc[f][0]));
+                    acc[f][1] = dp2a_hi_su(wp[2 * g + 1], q1, dp2a_lo_su(wp[2 * g], q1, acc[f][1]));
+                    acc[f][2] = dp2a_hi_su(wp[2 * g + 1], q2, dp2a_lo_su(wp[2 * g], q2, acc[f][2]));
+                }
             }
         }
-        const int c0 = min(max((int)acc0 >> 15, 0), 255), c1 = min(max((int)acc1 >> 15, 0), 255),
-                  c2 = min(max((int)acc2 >> 15, 0), 255);
-        return (uint32_t)c0 | ((uint32_t)c1 << 8) | ((uint32_t)c2 << 16);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            const int c0 = min(max((int)acc[f][0] >> 15, 0), 255), c1 = min(max((int)acc[f][1] >> 15, 0), 255),
+                      c2 = min(max((int)acc[f][2] >> 15, 0), 255);
+            out[f] = (uint32_t)c0 | ((uint32_t)c1 << 8) | ((uint32_t)c2 << 16);
+        }
+    }
+    __device__ static __forceinline__ uint32_t sample(uint32_t sbuf, const Pixel& p, uint32_t pitch) {
+        uint32_t out[1];
+        sample_frames<1>(sbuf, 0u, p, pitch, out);
+        return out[0];
     }
 };
 
@@ -377,6 +393,18 @@ __device__ __forceinline__ void dyn_range(double nmin, double nmax, double rad, 
     const int a = sat16(denorm_q<M>(nmin, rad, c) >> M::kShift), b = sat16(denorm_q<M>(nmax, rad, c) >> M::kShift);
     lo = min(a, b);
     hi = max(a, b);
+}
+
+// the FR frames of an item for one pixel; only modes with per-row state worth sharing implement sample_frames
+template <class M, int FR>
+__device__ __forceinline__ void sample_item(uint32_t sbuf, uint32_t frame_bytes, const typename M::Pixel& p, uint32_t pitch,
+                                            uint32_t (&out)[FR]) {
+    if constexpr (M::kInterp == VR180_INTER_LANCZOS4) {
+        M::template sample_frames<FR>(sbuf, frame_bytes, p, pitch, out);
+    } else {
+#pragma unroll
+        for (int f = 0; f < FR; ++f) out[f] = M::sample(sbuf + f * frame_bytes, p, pitch);
+    }
 }
 
 struct TileGeom {
@@ -530,8 +558,18 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
         }
         uint32_t word[FR][M::kPx];
 #pragma unroll
+        if (!DYN && M::kInterp == VR180_INTER_LANCZOS4) {  // a tap row's weights serve every frame of the item
+#pragma unroll
+            for (int k = 0; k < M::kPx; ++k) {
+                uint32_t r[FR];
+                sample_item<M, FR>(buf, (uint32_t)rect_bytes, pc[k], (uint32_t)pitch, r);
+#pragma unroll
+                for (int fr = 0; fr < FR; ++fr) res[fr][k] = r[fr];
+            }
+        }
+#pragma unroll
         for (int fr = 0; fr < FR; ++fr) {
-            if (!DYN) {
+            if (!DYN && M::kInterp != VR180_INTER_LANCZOS4) {
 #pragma unroll
                 for (int k = 0; k < M::kPx; ++k) res[fr][k] = M::sample(buf + fr * rect_bytes, pc[k], (uint32_t)pitch);
             }
