@@ -273,10 +273,10 @@ int launch_remap(const vr180_remap_params_t* p, cudaStream_t st) {
     // fast path: tiled, smem-staged kernel (tiled.cu); VR180_DISABLE_TILED=1 forces the generic gather (A/B tests)
     static const bool tiled_off = [] { const char* e = getenv("VR180_DISABLE_TILED"); return e && *e == '1'; }();
     if (!tiled_off) {
-        const short* tab_cubic = nullptr;
-        if (interp == VR180_INTER_CUBIC) VR180_CUDA(cudaGetSymbolAddress((void**)&tab_cubic, g_tab_cubic));
-        if (interp == VR180_INTER_LANCZOS4) VR180_CUDA(cudaGetSymbolAddress((void**)&tab_cubic, g_tab_lanczos));
-        const int rc = launch_remap_tiled(a, C, interp, *chains[0], *chains[1], tab_cubic, st);
+        const short* weight_tab = nullptr;
+        if (interp == VR180_INTER_CUBIC) VR180_CUDA(cudaGetSymbolAddress((void**)&weight_tab, g_weight_tab));
+        if (interp == VR180_INTER_LANCZOS4) VR180_CUDA(cudaGetSymbolAddress((void**)&weight_tab, g_tab_lanczos));
+        const int rc = launch_remap_tiled(a, C, interp, *chains[0], *chains[1], weight_tab, st);
         if (rc != VR180_ERR_UNSUPPORTED) return rc;
     }
 

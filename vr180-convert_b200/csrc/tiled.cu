@@ -1175,11 +1175,10 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
 }
 
 // Host-side eligibility + launch.  Returns VR180_ERR_UNSUPPORTED when the request is outside the fast path (the
-// caller then launches the generic k_remap); any other value is final.  `tab_cubic`: device copy of the 1024 x 16
-// bicubic weight table.
+// caller then launches the generic k_remap); any other value is final.  `weight_tab`: device copy of the weight table of
+// the requested interpolation (1024 x 16 bicubic, 1024 x 64 Lanczos4; unused otherwise).
 int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr180_chain_t& c0, const vr180_chain_t& c1,
-                       const short* tab_cubic, cudaStream_t st) {
-    // `tab_cubic`: the weight table of the requested interpolation (1024 x 16 bicubic or 1024 x 64 Lanczos4)
+                       const short* weight_tab, cudaStream_t st) {
     if (channels != 3 || a0.border_mode != VR180_BORDER_CONSTANT) return VR180_ERR_UNSUPPORTED;
     if (interp != VR180_INTER_NEAREST && interp != VR180_INTER_LINEAR && interp != VR180_INTER_CUBIC &&
         interp != VR180_INTER_LANCZOS4)
@@ -1225,16 +1224,16 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
         return pairs ? launch_mode<tiled::Linear, false, 2>(a0, c0, c1, nullptr, st)
                      : launch_mode<tiled::Linear, false, 1>(a0, c0, c1, nullptr, st);
     }
-    if (!tab_cubic) return VR180_ERR_UNSUPPORTED;
+    if (!weight_tab) return VR180_ERR_UNSUPPORTED;
     if (interp == VR180_INTER_LANCZOS4) {
-        if (dyn) return launch_mode<tiled::Lanczos4, true, 1>(a0, c0, c1, tab_cubic, st);
-        return pairs ? launch_mode<tiled::Lanczos4, false, 2>(a0, c0, c1, tab_cubic, st)
-                     : launch_mode<tiled::Lanczos4, false, 1>(a0, c0, c1, tab_cubic, st);
+        if (dyn) return launch_mode<tiled::Lanczos4, true, 1>(a0, c0, c1, weight_tab, st);
+        return pairs ? launch_mode<tiled::Lanczos4, false, 2>(a0, c0, c1, weight_tab, st)
+                     : launch_mode<tiled::Lanczos4, false, 1>(a0, c0, c1, weight_tab, st);
     }
-    if (dyn) return launch_mode<tiled::Cubic, true, 1>(a0, c0, c1, tab_cubic, st);
-    if (frames_per_cta(tiles, a0.n_frames) >= 8) return launch_mode<tiled::Cubic, false, 4>(a0, c0, c1, tab_cubic, st);
-    return pairs ? launch_mode<tiled::Cubic, false, 2>(a0, c0, c1, tab_cubic, st)
-                 : launch_mode<tiled::Cubic, false, 1>(a0, c0, c1, tab_cubic, st);
+    if (dyn) return launch_mode<tiled::Cubic, true, 1>(a0, c0, c1, weight_tab, st);
+    if (frames_per_cta(tiles, a0.n_frames) >= 8) return launch_mode<tiled::Cubic, false, 4>(a0, c0, c1, weight_tab, st);
+    return pairs ? launch_mode<tiled::Cubic, false, 2>(a0, c0, c1, weight_tab, st)
+                 : launch_mode<tiled::Cubic, false, 1>(a0, c0, c1, weight_tab, st);
 }
 
 }  // namespace vr180
