@@ -490,9 +490,9 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
             const int o = n & (OB - 1);
             const int v = (NV == 2) ? (n & 1) : 0, f = f0 + FR * ((NV == 2) ? (n >> 1) : n);
             mbar_wait(s_ofull + o * 8, (uint32_t)(n / OB) & 1u);  // every sampling warp has written item n
+            if (n + S < n_items) load();  // ofull(n) also means: every warp has left the stage of item n -> re-fill it
             tma_store_3d(&tm.dst, v ? dst_x1 : dst_x0, tg.y0, f, s_out + o * kOutItemBytes);
             bulk_commit();
-            if (n + S < n_items) load();  // ofull(n) also means: every warp has left the stage of item n -> re-fill it
             // hand the out buffer back as soon as the store has read it (the next ofull is an item time away, so
             // the producer has nothing else to do): a sampling warp may then run OB items ahead of the slowest one
             bulk_wait_read<0>();
