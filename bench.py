@@ -411,6 +411,11 @@ def run_gpu(args) -> dict:
     torch.cuda.set_device(local)
     V.set_device(local)
     device = torch.device("cuda", local)
+    if world > 1:  # one process per GPU: keep the rank and its pinned staging buffers on the GPU's NUMA node
+        from vr180_convert_b200.shard import bind_host_near_gpu
+
+        bound = bind_host_near_gpu(local)
+        print(f"[rank {rank}] host CPUs near GPU {local}: {len(bound) if bound else 'unchanged'}", file=sys.stderr)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod

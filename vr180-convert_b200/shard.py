@@ -35,3 +35,33 @@ def gather_shards(rng: range, dist=None, device="cpu") -> list[range]:
     out = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
     dist.all_gather(out, mine)
     return [range(int(o[0]), int(o[1])) for o in out]
+
+
+def bind_host_near_gpu(device_index: int) -> list[int] | None:
+    """One process per GPU: run this process (and therefore first-touch its pinned staging buffers) on the CPUs of
+    the NUMA node the GPU hangs off, read from sysfs (`/sys/bus/pci/devices/<bdf>/local_cpulist`).  With 8 ranks on a
+    two-socket host the host<->device copies of `vr180_ctx_run` otherwise cross the socket interconnect for half of
+    the GPUs.  Returns the CPU list it bound to, or None when the topology is not available (nothing is changed)."""
+    import os
+
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as fh:
+            spec = fh.read().strip()
+        cpus: set[int] = set()
+        for part in spec.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:  # noqa: BLE001 -- no sysfs / no such attribute / not permitted: leave the affinity alone
+        return None
