@@ -149,6 +149,19 @@ def test_shard_range_partitions_frames():
         V.shard_range(4, 2, 2)
 
 
+def test_bind_host_near_gpu_is_a_no_op_without_topology():
+    """No GPU / no sysfs entry: the NUMA binding helper reports None and leaves the affinity alone."""
+    import os
+
+    from vr180_convert_b200.shard import bind_host_near_gpu
+
+    before = os.sched_getaffinity(0)
+    bound = bind_host_near_gpu(0)
+    assert bound is None or set(bound) <= before
+    if bound is None:
+        assert os.sched_getaffinity(0) == before
+
+
 def test_argument_validation_without_gpu():
     with pytest.raises(ValueError):
         V.remap_maps(np.zeros((4, 4, 3), np.uint8), np.zeros((2, 2), np.float32), np.zeros((2, 2), np.float32),
