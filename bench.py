@@ -52,6 +52,9 @@ WORKLOADS = {
     "5k7_lut_linear": dict(n=2880, interp=1, tuple_=False, chain="base", src="lut_fixed", radius="fixed", pairs=64,
                            desc="batched 5.7K pairs (2x2880^2 -> 5760x2880), cached fixed-point LUT, INTER_LINEAR "
                                 "[BASELINE configs[3]]"),
+    "8k_nearest_fixed": dict(n=4096, interp=0, tuple_=False, chain="base", src="analytic", radius="fixed", pairs=16,
+                             desc="batched 8K pairs, base chain, fused analytic, INTER_NEAREST, fixed radius (the pipeline "
+                                  "without the interpolation arithmetic)"),
     "8k_cubic_fixed": dict(n=4096, interp=2, tuple_=False, chain="base", src="analytic", radius="fixed", pairs=16,
                            desc="batched 8K pairs, base chain, fused analytic, INTER_CUBIC, fixed radius"),
     "8k_lanczos4_fixed": dict(n=4096, interp=4, tuple_=False, chain="base", src="analytic", radius="fixed", pairs=16,
@@ -171,10 +174,14 @@ def touched_fraction(torch, maps, n_in: int, taps: int) -> float:
     """Unique source pixels touched by the interpolation footprint / source pixels (algorithmic input bytes)."""
     xm, ym = maps[0].reshape(-1), maps[1].reshape(-1)
     ok = torch.isfinite(xm) & torch.isfinite(ym)
-    sx = torch.round(xm[ok].double() * 32).long() >> 5
-    sy = torch.round(ym[ok].double() * 32).long() >> 5
+    if taps == 1:  # INTER_NEAREST: the pixel at cvRound(x), no sub-pixel grid
+        sx, sy = torch.round(xm[ok].double()).long(), torch.round(ym[ok].double()).long()
+        lo = hi = 0
+    else:
+        sx = torch.round(xm[ok].double() * 32).long() >> 5
+        sy = torch.round(ym[ok].double() * 32).long() >> 5
+        lo, hi = -(taps // 2 - 1), taps // 2
     touched = torch.zeros(n_in * n_in, dtype=torch.bool, device=maps.device)
-    lo, hi = -(taps // 2 - 1), taps // 2
     for dy in range(lo, hi + 1):
         for dx in range(lo, hi + 1):
             x, y = sx + dx, sy + dy
@@ -309,7 +316,7 @@ def run_workload(torch, V, wl_name: str, wl: dict, steps: int, warmup: int, dist
     mpix_step = pairs * n * 2 * n / 1e6
 
     # algorithmic bytes (DESIGN.md "roofline"): output written once + unique source pixels touched, per eye
-    taps = {0: 2, 1: 2, 2: 4, 4: 8}[wl["interp"]]
+    taps = {0: 1, 1: 2, 2: 4, 4: 8}[wl["interp"]]
     plan_for_maps = wp if not wp.auto_radius else V.SbsWarper(t, size_input=(n, n), size_output=(n, n),
                                                               interpolation=wl["interp"], radius=-(n // 2 - 8) - 0.5,
                                                               map_source="lut", device=device)
