@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VR180_ABI_VERSION 1
+#define VR180_ABI_VERSION 2
 
 typedef enum vr180_status {
     VR180_OK = 0,
@@ -258,10 +258,34 @@ typedef struct vr180_host_job {
     /* optional outputs (may be NULL): per (frame, view) transitions [n_frames*n_views*2] and per-frame radius */
     int32_t* transitions_out;
     double* radius_out;
+    /* Scattered frames -- apply()'s list of separate arrays (remapper.py:371-378, :388-398 loops over them with ONE
+       map): when src_frames[0] is non-NULL, frame f of view v starts at src_frames[v][f] (src[v] and
+       src_frame_stride[v] are ignored; src_pitch[v] still applies to every frame); when dst_frames is non-NULL,
+       destination frame f starts at dst_frames[f] (dst and dst_frame_stride are ignored). */
+    const uint8_t* const* src_frames[2];
+    uint8_t* const* dst_frames;
+    /* Host buffers that are not page-locked (plain NumPy arrays) cannot be DMA'd asynchronously: they are packed
+       into / unpacked from a pinned ring owned by the context by `copy_threads` host threads (0 = default:
+       min(8, cores / 4), or $VR180_COPY_THREADS), overlapped with the GPU work of the neighbouring chunks.
+       staging: VR180_STAGE_AUTO = per buffer, decided with cudaPointerGetAttributes; ALWAYS / NEVER force it. */
+    int32_t staging;
+    int32_t copy_threads;
 } vr180_host_job_t;
+
+enum { VR180_STAGE_AUTO = 0, VR180_STAGE_ALWAYS = 1, VR180_STAGE_NEVER = 2 };
 
 /* Synchronous: returns when every destination frame is complete in host memory. */
 int vr180_ctx_run(vr180_ctx_t* ctx, const vr180_host_job_t* job);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Test / profiling hooks (not part of the drop-in surface; no reference counterpart).
+ * ---------------------------------------------------------------------------------------------------- */
+/* The host-built OpenCV weight tables the kernels use (K = 4 bicubic, K = 8 Lanczos4): 1024*K*K int16. */
+int vr180_debug_weight_table(int K, int16_t* out);
+/* what 0: frames per CTA of the tiled kernel (0 = automatic) -- lets tests drive long frame loops (stage-ring
+   refills, mbarrier phase flips) with small outputs; what 1: tiled-kernel experiment flags (-1 = environment
+   variable VR180_TILED_DEBUG).  Returns the previous value. */
+int vr180_debug_set(int what, int value);
 
 #ifdef __cplusplus
 }

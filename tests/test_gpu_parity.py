@@ -310,11 +310,13 @@ def test_sbs_warper_per_eye_tuple_and_auto_radius():
 @pytest.mark.parametrize("interp", [0, 1, 2, 4])
 @pytest.mark.parametrize("per_eye", [False, True])
 def test_tiled_pipeline_ring_wraparound_and_source_edges(interp, per_eye):
-    """Stress of the tiled TMA pipeline (csrc/tiled.cu): an odd, long batch (stage ring, out-buffer ring and
-    mbarrier phases wrap several times), a radius larger than the source so that many tiles straddle the source
-    edge (TMA zero fill == BORDER_CONSTANT 0), tiles fully outside, partial edge tiles (output 208 x 104 is not a
+    """Source-edge handling of the tiled TMA kernel (csrc/tiled.cu) on an odd batch: a radius larger than the source
+    so that many tiles straddle the source edge (TMA zero fill == BORDER_CONSTANT 0), tiles fully outside, partial
+    edge tiles.  NOTE: with so few tiles the launcher gives every CTA ONE frame, so the stage ring is never re-filled
+    here -- the long frame loops (ring refills, mbarrier phase flips, > 1 frame per CTA with a per-frame radius) are
+    covered by tests/test_gpu_frameloop.py, which forces the frames per CTA.  (Output 208 x 104 is not a
     multiple of the 32 x 32 / 32 x 16 / 32 x 8 tiles; 208 * 3 bytes keeps the right eye's column offset 16-byte aligned,
-    which the TMA path needs), shared map (2 views per CTA) and per-eye maps (1 view per CTA)."""
+    which the TMA path needs.)  Shared map (2 views per CTA) and per-eye maps (1 view per CTA)."""
     import torch
 
     n, hin, win, wout, hout = 23, 192, 224, 208, 104
@@ -411,8 +413,9 @@ def test_tiled_per_frame_radius_equal_radii_take_fixed_pipeline(interp):
 
 @pytest.mark.parametrize("interp", [0, 1, 2, 4])
 def test_tiled_long_batch_many_ring_wraps(interp):
-    """131 frames (odd: two-frame items end with a phantom frame) through one launch: the stage ring, the out-buffer
-    ring and every mbarrier phase wrap dozens of times.  Every frame is checked against cv2.remap on the oracle's maps."""
+    """131 frames through one launch with the AUTOMATIC frames-per-CTA choice (6-12 tiles -> one frame per CTA, 131
+    frame chunks in grid.z): checks the chunk indexing over a long batch.  The ring-wrap regime itself is forced and
+    checked in tests/test_gpu_frameloop.py.  Every frame is compared with cv2.remap on the oracle's maps."""
     import torch
 
     n, hin, win, wout, hout = 131, 96, 128, 96, 64

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), f"{name} declared in include/vr180_b200.h but not exported"
         assert name in N.SYMBOLS, f"{name} has no ctypes prototype"
-    assert handle.vr180_abi_version() == 1
+    assert handle.vr180_abi_version() == N.ABI_VERSION == 2
     assert handle.vr180_status_string(-5) == b"malformed chain descriptor"
     assert isinstance(handle.vr180_launch_count(), int)
 
@@ -40,6 +40,37 @@ def test_struct_sizes_match_header_layout():
     assert C.sizeof(N.MapSrc) == 56
     assert C.sizeof(N.View) == 40 + 56 + 8
     assert C.sizeof(N.RemapParams) == 8 + 2 * 104 + 24 + 24
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """sizeof / offsetof of every ABI struct as gcc lays it out from include/vr180_b200.h == the ctypes mirror."""
+    import subprocess
+
+    fields = {"vr180_host_job_t": ("HostJob", ["n_frames", "src_pitch", "map_kind", "chain", "maps_cache_key", "threshold",
+                                               "border_value", "dst", "radius_out", "src_frames", "dst_frames", "staging",
+                                               "copy_threads"]),
+              "vr180_remap_params_t": ("RemapParams", ["view", "share_map", "border_value", "dst", "dst_frame_stride"]),
+              "vr180_view_t": ("View", ["map", "dst_x_offset"]),
+              "vr180_mapsrc_t": ("MapSrc", ["chain", "fixed", "map_pitch", "radius_dev"]),
+              "vr180_image_t": ("Image", ["pitch", "frame_stride"]),
+              "vr180_chain_t": ("Chain", ["ops"]),
+              "vr180_op_t": ("Op", ["p"])}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vr180_b200.h"', "int main(void) {"]
+    for cname, (_, fl) in fields.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in fl:
+            lines.append(f'printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, (pyname, fl) in fields.items():
+        cls = getattr(N, pyname)
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for f in fl:
+            assert int(got[f"{cname}.{f}"]) == getattr(cls, f).offset, (cname, f)
 
 
 def test_weight_tables_match_oracle():
@@ -122,6 +153,32 @@ def test_user_defined_transformer_is_opaque():
 
     assert Tweaked("equidistant").lower() is None
     assert V.FisheyeEncoder("equidistant").lower() == [("fisheye_enc", "equidistant")]
+
+    class MyMulti(V.MultiTransformer):  # containers that override the math are opaque too
+        def transform(self, x, y, **kwargs):
+            return x * 2, y
+
+    class MyInverse(V.InverseTransformer):
+        def transform(self, x, y, **kwargs):
+            return x, y * 2
+
+    assert MyMulti(transformers=[V.ZoomTransformer(2.0)]).lower() is None
+    assert MyInverse(V.FisheyeEncoder("equidistant")).lower() is None
+    assert (V.EquirectangularEncoder() * MyInverse(V.FisheyeEncoder("equidistant"))).lower() is None
+
+
+def test_transformers_are_sklearn_estimators_like_the_reference():
+    """transformer.py:11, :14-18: BaseEstimator + TransformerMixin."""
+    from sklearn.base import BaseEstimator, TransformerMixin, clone
+
+    t = V.PolynomialScaler([0, 1, -0.1])
+    assert isinstance(t, BaseEstimator) and isinstance(t, TransformerMixin)
+    assert t.get_params()["coefs_reverse"] == [0, 1, -0.1]
+    assert clone(V.ZoomTransformer(3.0)).scale == 3.0
+    z = V.ZoomTransformer(2.0)
+    z.set_params(scale=4.0)
+    assert z.lower() == [("zoom", 4.0)]
+    assert "transformers" in (V.ZoomTransformer(2.0) * V.EquirectangularEncoder()).get_params()
 
 
 def test_quaternion_helpers_match_scipy():

@@ -10,6 +10,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libvr180_b200.so"
 
+ABI_VERSION = 2
 MAX_OPS = 12
 MAX_OP_PARAMS = 12
 
@@ -63,7 +64,9 @@ class HostJob(C.Structure):
                 ("reserved1", C.c_int32), ("threshold", C.c_double), ("out_w", C.c_int32), ("out_h", C.c_int32),
                 ("interpolation", C.c_int32), ("border_mode", C.c_int32), ("border_value", C.c_uint8 * 4),
                 ("dst", C.c_void_p), ("dst_pitch", C.c_int64), ("dst_frame_stride", C.c_int64),
-                ("transitions_out", C.c_void_p), ("radius_out", C.c_void_p)]
+                ("transitions_out", C.c_void_p), ("radius_out", C.c_void_p),
+                ("src_frames", C.POINTER(C.c_void_p) * 2), ("dst_frames", C.POINTER(C.c_void_p)),
+                ("staging", C.c_int32), ("copy_threads", C.c_int32)]
 
 
 # every symbol include/vr180_b200.h declares: name -> (restype, argtypes)
@@ -89,6 +92,7 @@ SYMBOLS = {
     "vr180_host_unregister": (C.c_int, [C.c_void_p]),
     "vr180_ctx_run": (C.c_int, [C.c_void_p, C.POINTER(HostJob)]),
     "vr180_debug_weight_table": (C.c_int, [C.c_int, C.c_void_p]),
+    "vr180_debug_set": (C.c_int, [C.c_int, C.c_int]),
 }
 
 _lib = None
@@ -107,7 +111,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.vr180_abi_version() != 1:
+        if handle.vr180_abi_version() != ABI_VERSION:
             raise ImportError("libvr180_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

@@ -19,7 +19,7 @@ CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
 LIB = PKG / "libvr180_b200.so"
 OBJ_DIR = PKG / "build"
-SOURCES = ["kernels.cu", "tiled.cu", "api.cu"]
+SOURCES = ["kernels.cu", "tiled.cu", "api.cu", "pipeline.cu"]
 HEADERS = ["chain.cuh", "sampler.cuh", "tables.cuh", "common.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

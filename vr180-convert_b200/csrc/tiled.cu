@@ -1058,6 +1058,8 @@ static bool encode_u8_3d(CUtensorMap* out, const void* base, long long row_bytes
 
 // frames per CTA: the coordinates are evaluated once per CTA, so keep the chunk as large as the grid allows
 static int frames_per_cta(long long tiles, int n_frames) {
+    const int forced = g_debug_frames_per_cta.load(std::memory_order_relaxed);  // vr180_debug_set(0, n): tests
+    if (forced > 0) return forced < n_frames ? forced : n_frames;
     int fpc = n_frames;
     while (fpc > 1 && tiles * ((n_frames + fpc - 1) / fpc) < 148LL * 4 * 2) fpc = (fpc + 1) / 2;
     return fpc;
@@ -1149,8 +1151,9 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
     const int tiles_x = (a.W + kTileW - 1) / kTileW, tiles_y = (a.H + M::kTileH - 1) / M::kTileH;
     tp.tiles_x = tiles_x;
     tp.tab = tab;
-    static const int debug = [] { const char* e = getenv("VR180_TILED_DEBUG"); return e ? atoi(e) : 0; }();
-    tp.debug = debug;
+    static const int env_debug = [] { const char* e = getenv("VR180_TILED_DEBUG"); return e ? atoi(e) : 0; }();
+    const int set_debug = g_debug_tiled_flags.load(std::memory_order_relaxed);
+    tp.debug = set_debug >= 0 ? set_debug : env_debug;
     const long long tiles = (long long)tiles_x * tiles_y * n_groups;
     int fpc = frames_per_cta(tiles, a.n_frames);
     fpc = (fpc + FR - 1) / FR * FR;  // chunks start at multiples of FR: phantom frames can only lie past the batch

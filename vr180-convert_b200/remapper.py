@@ -8,7 +8,10 @@ CUDA device these functions raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
+import weakref
+from collections import OrderedDict
 from logging import getLogger
 from pathlib import Path
 from typing import Any, Literal, Sequence
@@ -47,6 +50,56 @@ def _ctx(device: int | None = None) -> C.c_void_p:
 
 
 # ---------------------------------------------------------------------------------------------------------
+# page-locked result arrays
+# ---------------------------------------------------------------------------------------------------------
+class _PinnedPool:
+    """Result frames are allocated in page-locked host memory (vr180_host_alloc), so the download of every frame is
+    a plain DMA into the array the caller receives -- no pageable bounce copy.  A buffer goes back to the pool when
+    the last NumPy view of it is garbage-collected; a video loop therefore recycles the same few buffers."""
+
+    def __init__(self, keep_bytes: int = 4 << 30) -> None:
+        self._free: dict[int, list[int]] = {}
+        self._free_bytes = 0
+        self._keep = keep_bytes
+        self._lock = threading.Lock()
+
+    def empty(self, shape: tuple[int, ...]) -> NDArray[np.uint8]:
+        nbytes = max(1, int(np.prod(shape)))
+        with self._lock:
+            lst = self._free.get(nbytes)
+            ptr = lst.pop() if lst else None
+            if ptr is not None:
+                self._free_bytes -= nbytes
+        if ptr is None:
+            handle = C.c_void_p()
+            N.check(N.lib().vr180_host_alloc(nbytes, C.byref(handle)), "vr180_host_alloc")
+            ptr = int(handle.value)
+        owner = (C.c_uint8 * nbytes).from_address(ptr)
+        weakref.finalize(owner, self._release, ptr, nbytes)
+        return np.frombuffer(owner, dtype=np.uint8, count=int(np.prod(shape))).reshape(shape)
+
+    def _release(self, ptr: int, nbytes: int) -> None:
+        with self._lock:
+            if self._free_bytes + nbytes <= self._keep:
+                self._free.setdefault(nbytes, []).append(ptr)
+                self._free_bytes += nbytes
+                return
+        try:
+            N.lib().vr180_host_free(C.c_void_p(ptr))
+        except Exception:  # noqa: BLE001 -- interpreter shutdown
+            pass
+
+
+_pinned = _PinnedPool()
+
+
+def _result_empty(shape: tuple[int, ...]) -> NDArray[np.uint8]:
+    if os.environ.get("VR180_PINNED_OUTPUTS", "1") == "0":
+        return np.empty(shape, dtype=np.uint8)
+    return _pinned.empty(shape)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # lowering helpers
 # ---------------------------------------------------------------------------------------------------------
 def full_chain(transformer: TransformerBase, *, radius: float, size_input: tuple[int, int]) -> TransformerBase:
@@ -62,6 +115,34 @@ def lower_full(transformer: TransformerBase, *, radius: float, size_input: tuple
     if ops is None or len(ops) > N.MAX_OPS:
         return None
     return ops
+
+
+_chain_cache: "OrderedDict[tuple, Any]" = OrderedDict()
+_chain_lock = threading.Lock()
+
+
+def lowered_chain(transformer: TransformerBase, *, radius: float, size_input: tuple[int, int],
+                  size_output: tuple[int, int]) -> "N.Chain | None":
+    """vr180_chain_t of Normalize * t * Denormalize, cached on repr(transformer) (the reference's transformers are
+    attrs classes with a stable repr) + radius + sizes: a video loop lowers its chain once, not once per frame."""
+    try:
+        key = (repr(transformer), float(radius), tuple(size_input), tuple(size_output))
+        hash(key)
+    except Exception:  # noqa: BLE001 -- exotic radius / repr: do not cache
+        key = None
+    if key is not None:
+        with _chain_lock:
+            if key in _chain_cache:
+                _chain_cache.move_to_end(key)
+                return _chain_cache[key]
+    ops = lower_full(transformer, radius=radius, size_input=size_input, size_output=size_output)
+    chain = N.make_chain(ops) if ops is not None else None
+    if key is not None:
+        with _chain_lock:
+            _chain_cache[key] = chain
+            while len(_chain_cache) > 64:
+                _chain_cache.popitem(last=False)
+    return chain
 
 
 def host_maps(transformer: TransformerBase, *, radius: float, size_input: tuple[int, int],
@@ -115,11 +196,13 @@ def _centre_line(img: NDArray) -> NDArray:
 
 
 def _device_radius(images: Sequence[NDArray], threshold: float = 10) -> list[float]:
+    """get_radius (transformer.py:108-140) of every image: the centre lines of all images of one geometry go up in
+    ONE upload, are scanned by ONE k_get_radius launch and come back with ONE blocking read."""
     import torch
 
     dev = torch.device("cuda", _default_device)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    out: list[float] = []
+    lines = []
     for img in images:
         line = _centre_line(np.asarray(img))
         if line.dtype != np.uint8:
@@ -130,15 +213,22 @@ def _device_radius(images: Sequence[NDArray], threshold: float = 10) -> list[flo
         # keep the reference's row-vs-column decision: a 1 x n line has cols > rows unless n == 1
         if cols <= rows and rows == 1:
             raise IndexError("index 0 is out of bounds for axis 0 with size 0")
-        d_line = torch.from_numpy(line).to(dev)
-        trans = torch.empty(2, dtype=torch.int32, device=dev)
-        im = N.Image(d_line.data_ptr(), rows, cols, ch, 0, cols * ch, rows * cols * ch)
-        N.check(N.lib().vr180_get_radius(C.byref(im), 1, 1, float(threshold), trans.data_ptr(), None, stream),
+        lines.append(line)
+    out: list[float] = [0.0] * len(lines)
+    groups: dict[tuple, list[int]] = {}
+    for i, line in enumerate(lines):
+        groups.setdefault(line.shape, []).append(i)
+    for (rows, cols, ch), idx in groups.items():
+        stack = np.stack([lines[i] for i in idx])  # (n, rows, cols, ch), one of rows / cols is 1
+        d_lines = torch.from_numpy(stack).to(dev)
+        trans = torch.empty((len(idx), 2), dtype=torch.int32, device=dev)
+        im = N.Image(d_lines.data_ptr(), rows, cols, ch, 0, cols * ch, rows * cols * ch)
+        N.check(N.lib().vr180_get_radius(C.byref(im), 1, len(idx), float(threshold), trans.data_ptr(), None, stream),
                 "vr180_get_radius")
-        first, last = (int(v) for v in trans.cpu())
-        if first < 0 or last < 0:
-            raise IndexError("index 0 is out of bounds for axis 0 with size 0")  # np.where(...)[0][0] on empty
-        out.append((last - first) / 2)
+        for i, (first, last) in zip(idx, trans.cpu().tolist()):
+            if first < 0 or last < 0:
+                raise IndexError("index 0 is out of bounds for axis 0 with size 0")  # np.where(...)[0][0] on empty
+            out[i] = (last - first) / 2
     return out
 
 
@@ -192,7 +282,7 @@ def _as_image(a: Any) -> NDArray:
 
 def warp_host(
     transformers: Sequence[TransformerBase],
-    images: Sequence[NDArray],
+    images: Sequence[Any],
     *,
     radii: Sequence[float],
     share_map: bool,
@@ -200,54 +290,93 @@ def warp_host(
     interpolation: int,
     border_mode: int,
     border_value: Any,
-) -> NDArray[np.uint8]:
-    """One host job: 1 or 2 views (eyes) of equal geometry -> one (H, n_views*W, C) frame (views side by side)."""
+    auto_radius: bool = False,
+    threshold: float = 10,
+) -> "NDArray[np.uint8] | list[NDArray[np.uint8]]":
+    """ONE host job (vr180_ctx_run) for a whole batch.
+
+    `images` holds one entry per view (1 = apply(), 2 = the eyes of apply_lr()); an entry is either one image or a
+    LIST of images of equal geometry (the frames of the batch: apply()'s image list, remapper.py:388-398; a clip of
+    stereo pairs).  Every frame is written as (H, n_views * W, C) with the views side by side.  Returns one array for
+    single images and a list of arrays (one per frame) for lists.
+
+    `auto_radius`: per-frame radius = max over the frame's views of get_radius (remapper.py:82-84 for one pair),
+    scanned and consumed on the device; a frame without a transition raises IndexError like the reference."""
     lib = N.lib()
-    views = [_as_image(im) for im in images]
-    rows, cols, ch = views[0].shape
-    for v in views[1:]:
-        if v.shape != views[0].shape:
-            raise ValueError("left and right images must have the same shape")
+    batched = isinstance(images[0], (list, tuple))
+    frames = [[_as_image(im) for im in (v if batched else [v])] for v in images]
+    n_views, n_frames = len(frames), len(frames[0])
+    if any(len(v) != n_frames for v in frames):
+        raise ValueError("every view needs the same number of frames")
+    if n_frames == 0:
+        return []
+    rows, cols, ch = frames[0][0].shape
+    for v in frames:
+        for im in v:
+            if im.shape != (rows, cols, ch):
+                raise ValueError("all frames / eyes of one job must have the same shape")
     w, h = int(size_output[0]), int(size_output[1])
-    n_views = len(views)
-    squeeze = np.asarray(images[0]).ndim == 2
-    dst = np.empty((h, w * n_views, ch), dtype=np.uint8)
+    first = np.asarray(images[0][0] if batched else images[0])
+    squeeze = first.ndim == 2
+    outs = [_result_empty((h, w * n_views, ch)) for _ in range(n_frames)]
 
     job = N.HostJob()
-    job.n_views, job.n_frames = n_views, 1
+    job.n_views, job.n_frames = n_views, n_frames
     job.src_rows, job.src_cols, job.channels = rows, cols, ch
-    keep: list[Any] = []
+    keep: list[Any] = [frames]
     n_maps = 1 if (share_map or n_views == 1) else n_views
-    lowered = [lower_full(transformers[m], radius=radii[m], size_input=(rows, cols), size_output=(w, h))
-               for m in range(n_maps)]
-    analytic = all(o is not None for o in lowered)
+    chains = [lowered_chain(transformers[m], radius=(1.0 if auto_radius else radii[m]), size_input=(rows, cols),
+                            size_output=(w, h)) for m in range(n_maps)]
+    analytic = all(c is not None for c in chains)
+    if auto_radius and not analytic:
+        raise ValueError("a per-frame radius is consumed on the device by lowerable transformer chains only")
     job.map_kind = N.MAPSRC_ANALYTIC if analytic else N.MAPSRC_FLOAT2
     job.share_map = 1 if (share_map and n_views == 2) else 0
     for m in range(n_maps):
         if analytic:
-            chain = N.make_chain(lowered[m])
-            keep.append(chain)
-            job.chain[m] = C.pointer(chain)
+            job.chain[m] = C.pointer(chains[m])
+            keep.append(chains[m])
         else:
-            xm, ym = (get_map if lowered[m] is not None else host_maps)(
+            xm, ym = (get_map if chains[m] is not None else host_maps)(
                 transformers[m], radius=radii[m], size_input=(rows, cols), size_output=(w, h))
             xm, ym = np.ascontiguousarray(xm), np.ascontiguousarray(ym)
             keep += [xm, ym]
             job.xmap[m], job.ymap[m] = xm.ctypes.data, ym.ctypes.data
-    for v, img in enumerate(views):
-        job.src[v] = img.ctypes.data
-        job.src_pitch[v] = img.strides[0]
-        job.src_frame_stride[v] = img.strides[0] * rows
+    for v in range(n_views):
+        # the job carries one row pitch per view: a view whose frames disagree is made contiguous
+        pitch = frames[v][0].strides[0]
+        if any(im.strides[0] != pitch for im in frames[v]):
+            frames[v] = [np.ascontiguousarray(im) for im in frames[v]]
+            pitch = frames[v][0].strides[0]
+        ptrs = (C.c_void_p * n_frames)(*[im.ctypes.data for im in frames[v]])
+        keep.append(ptrs)
+        job.src[v] = ptrs[0]
+        job.src_frames[v] = ptrs
+        job.src_pitch[v] = pitch
+        job.src_frame_stride[v] = pitch * rows
     job.out_w, job.out_h = w, h
     job.interpolation, job.border_mode = interpolation, border_mode
     for i, b in enumerate(_border_bytes(border_value, ch)):
         job.border_value[i] = b
-    job.dst = dst.ctypes.data
-    job.dst_pitch = dst.strides[0]
-    job.dst_frame_stride = dst.strides[0] * h
+    dptrs = (C.c_void_p * n_frames)(*[o.ctypes.data for o in outs])
+    keep.append(dptrs)
+    job.dst = dptrs[0]
+    job.dst_frames = dptrs
+    job.dst_pitch = outs[0].strides[0]
+    job.dst_frame_stride = outs[0].strides[0] * h
+    trans = None
+    if auto_radius:
+        job.radius_mode = 1
+        job.threshold = float(threshold)
+        trans = np.empty((n_frames, n_views, 2), dtype=np.int32)
+        job.transitions_out = trans.ctypes.data
     N.check(lib.vr180_ctx_run(_ctx(), C.byref(job)), "vr180_ctx_run")
     del keep
-    return dst[:, :, 0] if squeeze else dst
+    if trans is not None and (trans < 0).any():
+        raise IndexError("index 0 is out of bounds for axis 0 with size 0")  # get_radius found no transition
+    if squeeze:
+        outs = [o[:, :, 0] for o in outs]
+    return outs if batched else outs[0]
 
 
 def _imread(path: Any) -> NDArray:
@@ -274,7 +403,10 @@ def apply(
     radius: float | Literal["auto", "max"] = "auto",
 ) -> Sequence[NDArray[np.uint8]]:
     """Remap every input image with ONE map built from images[0]'s shape (remapper.py:324-403).
-    Argument names (including the `boarder_*` spelling) are the reference's."""
+    Argument names (including the `boarder_*` spelling) are the reference's.
+
+    All images of the call go through ONE host job (one radius scan launch, one chain lowering, uploads / warps /
+    downloads of neighbouring images overlapped) instead of the reference's per-image cv.remap loop."""
     in_list = [in_paths] if isinstance(in_paths, (str, Path, np.ndarray)) else list(in_paths)
     out_list = [out_paths] if isinstance(out_paths, (str, Path)) else out_paths
     interpolation, border_mode = _check_modes(interpolation, boarder_mode)
@@ -282,14 +414,20 @@ def apply(
     images = [_imread(p) if isinstance(p, (str, Path)) else p for p in in_list]
     radius_ = get_radius_smart(radius, images)
     size_in = (images[0].shape[0], images[0].shape[1])
-    results = []
-    for img in images:
-        if np.asarray(img).shape[:2] != size_in:
+    same = [i for i, img in enumerate(images) if np.asarray(img).shape == np.asarray(images[0]).shape]
+    results: list[Any] = [None] * len(images)
+    warped = warp_host([transformer], [[images[i] for i in same]], radii=[radius_], share_map=True,
+                       size_output=size_output, interpolation=interpolation, border_mode=border_mode,
+                       border_value=boarder_value)
+    for i, r in zip(same, warped):
+        results[i] = r
+    for i, img in enumerate(images):
+        if results[i] is None:
             # the reference samples a differently-sized image with images[0]'s map; keep that behaviour
             LOG.warning("image shape %s differs from the first image %s; using the first image's map",
                         np.asarray(img).shape, size_in)
-        results.append(_warp_with_first_geometry(transformer, img, size_in, radius_, size_output, interpolation,
-                                                 border_mode, boarder_value))
+            results[i] = _warp_with_first_geometry(transformer, img, size_in, radius_, size_output, interpolation,
+                                                   border_mode, boarder_value)
     if out_list is not None:
         for to_path, image in zip(out_list, results):
             _imwrite(to_path, image)
@@ -317,7 +455,7 @@ def remap_maps(img: NDArray, xmap: NDArray, ymap: NDArray, *, interpolation: int
     view = _as_image(img)
     rows, cols, ch = view.shape
     h, w = xm.shape
-    dst = np.empty((h, w, ch), dtype=np.uint8)
+    dst = _result_empty((h, w, ch))
     job = N.HostJob()
     job.n_views = job.n_frames = 1
     job.src[0] = view.ctypes.data
@@ -375,18 +513,65 @@ def apply_lr(
     LOG.info(f"Saved to {Path(out_path).absolute()}")
 
 
+def _split_if_same_path(left, right):
+    if isinstance(left, (str, Path)) and isinstance(right, (str, Path)) and left == right:
+        image = _imread(left)  # one SBS source file: split into halves (views, not copies) -- remapper.py:448-456
+        return image[:, : image.shape[1] // 2], image[:, image.shape[1] // 2:]
+    return left, right
+
+
 def lr_frame(transformer, left, right, *, size_output=(2048, 2048), interpolation=INTER_LANCZOS4,
              boarder_mode=BORDER_CONSTANT, boarder_value=0, radius="auto") -> NDArray[np.uint8]:
     """The in-memory part of apply_lr: returns the (H, 2W, C) SBS frame."""
     interpolation, border_mode = _check_modes(interpolation, boarder_mode)
-    if isinstance(left, (str, Path)) and isinstance(right, (str, Path)) and left == right:
-        image = _imread(left)  # one SBS source file: split into halves (views, not copies) -- remapper.py:448-456
-        left, right = image[:, : image.shape[1] // 2], image[:, image.shape[1] // 2:]
+    left, right = _split_if_same_path(left, right)
     eyes = [_imread(p) if isinstance(p, (str, Path)) else p for p in (left, right)]
+    kw = dict(size_output=size_output, interpolation=interpolation, border_mode=border_mode, border_value=boarder_value)
+    same_shape = np.asarray(eyes[0]).shape == np.asarray(eyes[1]).shape
     if isinstance(transformer, tuple):  # per-eye transformer: own radius and own map per eye (remapper.py:460-473)
         radii = [get_radius_smart(radius, [eye]) for eye in eyes]
-        return warp_host(list(transformer), eyes, radii=radii, share_map=False, size_output=size_output,
-                         interpolation=interpolation, border_mode=border_mode, border_value=boarder_value)
+        if same_shape:
+            return warp_host(list(transformer), eyes, radii=radii, share_map=False, **kw)
+        # eyes of different geometry (unequal crops): the reference runs apply() per eye with that eye's size_input
+        halves = [warp_host([t], [eye], radii=[r], share_map=True, **kw) for t, eye, r in zip(transformer, eyes, radii)]
+        return np.concatenate(halves, axis=1)
     radius_ = get_radius_smart(radius, eyes)  # one radius = max over both eyes, ONE map (remapper.py:475-484)
-    return warp_host([transformer], eyes, radii=[radius_], share_map=True, size_output=size_output,
-                     interpolation=interpolation, border_mode=border_mode, border_value=boarder_value)
+    if same_shape:
+        return warp_host([transformer], eyes, radii=[radius_], share_map=True, **kw)
+    # the reference builds the map from the LEFT image's shape and samples the right image with it (remapper.py:385)
+    size_in = (np.asarray(eyes[0]).shape[0], np.asarray(eyes[0]).shape[1])
+    halves = [_warp_with_first_geometry(transformer, eye, size_in, radius_, size_output, interpolation, border_mode,
+                                        boarder_value) for eye in eyes]
+    return np.concatenate(halves, axis=1)
+
+
+def lr_frames(transformer, lefts: Sequence[Any], rights: Sequence[Any], *, size_output=(2048, 2048),
+              interpolation=INTER_LANCZOS4, boarder_mode=BORDER_CONSTANT, boarder_value=0,
+              radius="auto") -> "list[NDArray[np.uint8]]":
+    """apply_lr's in-memory part for a CLIP: `lefts[i]`, `rights[i]` -> SBS frame i, every pair exactly as
+    `lr_frame` would produce it (per-pair radius for radius="auto": the max over the pair's eyes,
+    remapper.py:82-84, :475-484), but as ONE host job -- uploads, warps and downloads of neighbouring pairs overlap.
+    Pairs must share one geometry.  A per-eye transformer tuple with radius="auto" needs a radius per EYE
+    (remapper.py:460-473) and is processed pair by pair."""
+    interpolation, border_mode = _check_modes(interpolation, boarder_mode)
+    if len(lefts) != len(rights):
+        raise ValueError("lefts / rights differ in length")
+    lefts = [_imread(p) if isinstance(p, (str, Path)) else p for p in lefts]
+    rights = [_imread(p) if isinstance(p, (str, Path)) else p for p in rights]
+    if not lefts:
+        return []
+    kw = dict(size_output=size_output, interpolation=interpolation, border_mode=border_mode, border_value=boarder_value)
+    auto = isinstance(radius, str) and radius == "auto"
+    shapes = {np.asarray(im).shape for im in (*lefts, *rights)}
+    per_eye = isinstance(transformer, tuple)
+    lowerable = all(t.lower(shape=(int(size_output[1]), int(size_output[0]))) is not None
+                    for t in (transformer if per_eye else (transformer,)))
+    if len(shapes) != 1 or (auto and (per_eye or not lowerable)):
+        return [lr_frame(transformer, le, ri, size_output=size_output, interpolation=interpolation,
+                         boarder_mode=boarder_mode, boarder_value=boarder_value, radius=radius)
+                for le, ri in zip(lefts, rights)]
+    ts = list(transformer) if per_eye else [transformer]
+    if auto:
+        return warp_host(ts, [lefts, rights], radii=[1.0] * len(ts), share_map=not per_eye, auto_radius=True, **kw)
+    radius_ = get_radius_smart(radius, [lefts[0], rights[0]])  # "max" / a number: the same for every pair
+    return warp_host(ts, [lefts, rights], radii=[radius_] * len(ts), share_map=not per_eye, **kw)

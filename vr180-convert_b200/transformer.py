@@ -16,6 +16,7 @@ from typing import Any, Generic, Literal, Sequence, TypeVar
 import attrs
 import numpy as np
 from numpy.typing import NDArray
+from sklearn.base import BaseEstimator, TransformerMixin
 
 from . import hostmath
 from .quat import quaternion, rotation_matrix
@@ -29,8 +30,11 @@ def _unknown_mapping(name: Any) -> ValueError:
                       "'rectilinear', 'stereographic', 'equidistant', 'equisolid', 'orthographic'.")
 
 
-class TransformerBase(metaclass=ABCMeta):
-    """Coordinate transformer: new_image[(x, y)] = old_image[transform(x, y)]  (transformer.py:14-81)."""
+class TransformerBase(BaseEstimator, TransformerMixin, metaclass=ABCMeta):
+    """Coordinate transformer: new_image[(x, y)] = old_image[transform(x, y)]  (transformer.py:14-81).
+    As in the reference the base is a scikit-learn estimator (transformer.py:11, :14-18): `get_params` /
+    `set_params` / `clone` work on every transformer, and `repr` of the attrs subclasses is the cache key of
+    a lowered chain (remapper.lowered_chain)."""
 
     @abstractmethod
     def transform(self, x: NDArray, y: NDArray, **kwargs: Any) -> tuple[NDArray, NDArray]:
@@ -93,6 +97,8 @@ class MultiTransformer(TransformerBase):
         return x, y
 
     def lower(self, shape=None, inverse=False):
+        if not _pristine(self, MultiTransformer, "transform", "inverse_transform"):
+            return None  # a subclass re-defined the composition in Python: opaque, host LUT route
         out: list[tuple] = []
         for t in (self.transformers[::-1] if inverse else self.transformers):
             ops = t.lower(shape=shape, inverse=inverse)
@@ -246,6 +252,8 @@ class InverseTransformer(TransformerBase, Generic[T]):
         return self.transformer.transform(x, y, **kwargs)
 
     def lower(self, shape=None, inverse=False):
+        if not _pristine(self, InverseTransformer, "transform", "inverse_transform"):
+            return None
         return self.transformer.lower(shape=shape, inverse=not inverse)
 
 
