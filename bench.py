@@ -52,6 +52,9 @@ WORKLOADS = {
     "5k7_lut_linear": dict(n=2880, interp=1, tuple_=False, chain="base", src="lut_fixed", radius="fixed", pairs=64,
                            desc="batched 5.7K pairs (2x2880^2 -> 5760x2880), cached fixed-point LUT, INTER_LINEAR "
                                 "[BASELINE configs[3]]"),
+    "5k7_lut_linear_512": dict(n=2880, interp=1, tuple_=False, chain="base", src="lut_fixed", radius="fixed", pairs=512,
+                               desc="512 resident 5.7K pairs per GPU (51 GB in + 51 GB out), cached fixed-point LUT, "
+                                    "INTER_LINEAR, one launch [BASELINE configs[3]: 1024 pairs over >= 2 GPUs]"),
     "8k_nearest_fixed": dict(n=4096, interp=0, tuple_=False, chain="base", src="analytic", radius="fixed", pairs=16,
                              desc="batched 8K pairs, base chain, fused analytic, INTER_NEAREST, fixed radius (the pipeline "
                                   "without the interpolation arithmetic)"),
@@ -158,15 +161,18 @@ def synth_frames_torch(torch, n_frames: int, n: int, seed: int, device, vary_mar
     distance between two noise pixels (0.5 ...) instead of the disc radius -(R + 0.5)."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    frames = torch.randint(16, 256, (n_frames, n, n, 3), dtype=torch.uint8, device=device, generator=g)
+    frames = torch.empty((n_frames, n, n, 3), dtype=torch.uint8, device=device)
     yy = torch.arange(n, device=device).view(n, 1)
     xx = torch.arange(n, device=device).view(1, n)
     r2 = (xx - n // 2) ** 2 + (yy - n // 2) ** 2
-    if vary_margin:  # every frame gets a different disc radius (margin 8, 12, 16, 20, 8, ...)
-        for i in range(n_frames):
-            frames[i, r2 > (n // 2 - 8 - 4 * (i % 4)) ** 2] = 0
-    else:
-        frames[:, r2 > (n // 2 - 8) ** 2] = 0
+    for i0 in range(0, n_frames, 32):  # chunks: a 512-pair batch must not need a second copy of itself
+        part = frames[i0:i0 + 32]
+        part.copy_(torch.randint(16, 256, tuple(part.shape), dtype=torch.uint8, device=device, generator=g))
+        if vary_margin:  # every frame gets a different disc radius (margin 8, 12, 16, 20, 8, ...)
+            for i in range(part.shape[0]):
+                part[i, r2 > (n // 2 - 8 - 4 * ((i0 + i) % 4)) ** 2] = 0
+        else:
+            part[:, r2 > (n // 2 - 8) ** 2] = 0
     return frames
 
 
@@ -193,6 +199,42 @@ def touched_fraction(torch, maps, n_in: int, taps: int) -> float:
 # ---------------------------------------------------------------------------------------------------------
 # CPU reference path (oracle port: NumPy chain restatement + the real cv2.remap + concatenate)
 # ---------------------------------------------------------------------------------------------------------
+_ORACLE_MAPS: dict = {}
+
+
+def oracle_maps(wl: dict):
+    """The reference's maps for this workload from the NumPy restatement (oracle/chain_np.py), built once per process:
+    [(xmap, ymap)] per eye-map, and the seconds the (single-threaded) build took."""
+    from oracle import chain_np
+
+    key = (wl["chain"], wl["tuple_"], wl["n"])
+    if key not in _ORACLE_MAPS:
+        n = wl["n"]
+        t0 = time.perf_counter()
+        n_maps = 2 if wl["tuple_"] else 1
+        # radius: the fixed-radius workloads use n / 2; the "auto" ones get_radius of the synthetic disc = -(n/2 - 8) - 0.5
+        radius = n / 2 if wl["radius"] == "fixed" else -(n // 2 - 8) - 0.5
+        maps = [chain_np.get_map(oracle_ops(wl["chain"], conj=(m == 0 and wl["tuple_"])), radius=radius,
+                                 size_input=(n, n), size_output=(n, n)) for m in range(n_maps)]
+        _ORACLE_MAPS[key] = (maps, time.perf_counter() - t0)
+    return _ORACLE_MAPS[key]
+
+
+CV_INTERP = {0: 0, 1: 1, 2: 2, 4: 4}  # cv2.INTER_NEAREST / LINEAR / CUBIC / LANCZOS4 are the API's integers
+
+
+def oracle_sbs(wl: dict, left: np.ndarray, right: np.ndarray) -> np.ndarray:
+    """What the reference produces for one pair: cv2.remap per eye on the oracle's maps + np.concatenate."""
+    import cv2
+
+    maps, _ = oracle_maps(wl)
+    eyes = []
+    for e, img in enumerate((left, right)):
+        xm, ym = maps[e if len(maps) == 2 else 0]
+        eyes.append(cv2.remap(img, xm, ym, interpolation=CV_INTERP[wl["interp"]], borderMode=cv2.BORDER_CONSTANT, borderValue=0))
+    return np.concatenate(eyes, axis=1)
+
+
 def cpu_reference_setup(wl: dict, sample_pairs: int):
     import cv2
 
@@ -206,12 +248,9 @@ def cpu_reference_setup(wl: dict, sample_pairs: int):
         img = np.random.default_rng(i).integers(16, 256, (n, n, 3), dtype=np.uint8)
         img[outside] = 0
         rng_frames.append(img)
-    t0 = time.perf_counter()
-    n_maps = 2 if wl["tuple_"] else 1
-    maps = [chain_np.get_map(oracle_ops(wl["chain"], conj=(m == 0 and wl["tuple_"])), radius=n / 2, size_input=(n, n),
-                             size_output=(n, n)) for m in range(n_maps)]
-    t_maps = time.perf_counter() - t0
-    interp = {1: cv2.INTER_LINEAR, 2: cv2.INTER_CUBIC}[wl["interp"]]
+    maps, t_maps = oracle_maps(wl)
+    n_maps = len(maps)
+    interp = CV_INTERP[wl["interp"]]
 
     def step():
         for p in range(sample_pairs):
@@ -285,7 +324,7 @@ def time_device(torch, fn, steps: int, warmup: int, dist):
 
 
 def run_workload(torch, V, wl_name: str, wl: dict, steps: int, warmup: int, dist, pairs: int | None = None,
-                 want_e2e: bool = True, device=None):
+                 want_e2e: bool = True, device=None, check_frames=()):
     n = wl["n"]
     pairs = pairs or wl["pairs"]
     ring = 1
@@ -332,11 +371,19 @@ def run_workload(torch, V, wl_name: str, wl: dict, steps: int, warmup: int, dist
            "launches_per_step": launches_per_step, "bytes_per_step": bytes_step, "touched_fraction": frac_in,
            "ring": ring}
 
+    if check_frames:
+        # parity of the TIMED regime: frames of the batch launch itself (not of a separate small launch) go to the
+        # host, where run_gpu compares them with cv2.remap on the oracle's maps
+        wp(left[:pairs], right[:pairs], out=out[:pairs])
+        torch.cuda.synchronize()
+        res["samples"] = [(f, left[f].cpu().numpy(), right[f].cpu().numpy(), out[f].cpu().numpy())
+                          for f in sorted({min(max(f, 0), pairs - 1) for f in check_frames})]
+
     if want_e2e:
         import ctypes as C
 
         N = V._native
-        pe = min(pairs, 16)
+        pe = min(pairs, 32)
         nbytes_in, nbytes_out = pe * n * n * 3, pe * n * 2 * n * 3
         ptrs = []
         for nb in (nbytes_in, nbytes_in, nbytes_out):
@@ -378,28 +425,66 @@ def run_workload(torch, V, wl_name: str, wl: dict, steps: int, warmup: int, dist
         def e2e_step():
             N.check(lib.vr180_ctx_run(handle, C.byref(job)), "vr180_ctx_run")
 
-        for _ in range(2):
-            e2e_step()
-        if dist is not None:
-            dist.barrier()
+        def timed_host(fn, reps):
+            for _ in range(2):
+                fn()
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()  # synchronous: returns when every SBS frame is in host memory
+            dt = (time.perf_counter() - t0) / reps
+            if dist is not None:
+                tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            return dt
+
         e_steps = max(3, min(steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            e2e_step()  # synchronous: returns when every SBS frame is in host memory
-        dt = (time.perf_counter() - t0) / e_steps
-        if dist is not None:
-            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        # spot check: the host path produced the same frame as the device-resident path
-        same = bool(np.array_equal(h_o[0], out[0].cpu().numpy())) if ring == 1 or True else True
+        dt = timed_host(e2e_step, e_steps)
         res["e2e"] = {"value": pe * n * 2 * n / 1e6 / dt, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * nbytes_in,
                       "d2h_bytes_per_step": nbytes_out, "pairs_per_step": pe, "ms_per_step": dt * 1e3,
-                      "matches_device_path": same, "api": "vr180_ctx_run (C ABI host call behind apply_lr/SbsWarper)"}
+                      "api": "vr180_ctx_run (the C-ABI host call behind apply / apply_lr / lr_frames), page-locked host buffers"}
+        res["e2e_frame0"] = h_o[0].copy()  # compared with the oracle by run_gpu
+
+        # copy-only ceiling of the same traffic: page-locked H2D + D2H, no kernel, both directions at once; under
+        # torchrun every rank measures at the same time, so the sum is the box's ceiling for N GPUs
+        rates = (C.c_double * 4)()
+        if dist is not None:
+            dist.barrier()
+        N.check(lib.vr180_debug_copy_ceiling(torch.cuda.current_device(), 256 << 20, 12, rates), "copy_ceiling")
+        t_pair = max(2 * n * n * 3 / (rates[2] * 1e9), n * 2 * n * 3 / (rates[3] * 1e9))
+        res["e2e"].update({"copy_ceiling": n * 2 * n / 1e6 / t_pair, "frac_of_ceiling": res["e2e"]["value"] / (n * 2 * n / 1e6 / t_pair),
+                           "copy_gbs": {"h2d_alone": rates[0], "d2h_alone": rates[1], "h2d_concurrent": rates[2],
+                                        "d2h_concurrent": rates[3]},
+                           "copy_ceiling_note": "Mpix/s if the pair's 2 source frames (H2D) and its SBS frame (D2H) moved at "
+                                                "the measured concurrent page-locked copy rates with no kernel and no "
+                                                "pipeline fill / drain"})
         lib.vr180_ctx_destroy(handle)
         for p in ptrs:
             lib.vr180_host_free(p)
-        del keep
+        del keep, h_l, h_r, h_o
+
+        # the same metric through the PYTHON API on plain (pageable) NumPy arrays: V.lr_frames = apply_lr's in-memory
+        # part for a clip, one host job; the sources are packed into the context's pinned ring by copy threads, the
+        # SBS frames are returned as page-locked arrays
+        lefts = [left[i].cpu().numpy() for i in range(pe)]
+        rights = [right[i].cpu().numpy() for i in range(pe)]
+        py_radius = "auto" if wl["radius"] == "auto" else n / 2
+        state_py = {}
+
+        def py_step():
+            state_py["out"] = V.lr_frames(t, lefts, rights, size_output=(n, n), interpolation=wl["interp"], radius=py_radius)
+
+        dtp = timed_host(py_step, max(3, min(steps, 5)))
+        res["e2e_python_api"] = {"value": pe * n * 2 * n / 1e6 / dtp, "unit": "Mpix/s", "pairs_per_step": pe,
+                                 "ms_per_step": dtp * 1e3, "h2d_bytes_per_step": 2 * nbytes_in,
+                                 "d2h_bytes_per_step": nbytes_out,
+                                 "api": "vr180_convert_b200.lr_frames(transformer, [ndarray...], [ndarray...]) on pageable "
+                                        "NumPy arrays (apply_lr's in-memory part for a clip)",
+                                 "vs_c_abi": (pe * n * 2 * n / 1e6 / dtp) / res["e2e"]["value"]}
+        res["e2e_python_frame0"] = np.array(state_py["out"][0])
+        del lefts, rights, state_py
     del left, right, out, wp
     torch.cuda.empty_cache()
     return res
@@ -436,8 +521,11 @@ def run_gpu(args) -> dict:
     if rank == 0:
         sampler.start()
     launches0 = lib.vr180_launch_count()
+    want_parity = rank == 0 and world == 1 and not args.no_cpu_baseline
+    n_pairs = args.pairs or wl["pairs"]
     main = run_workload(torch, V, args.workload, wl, args.steps, args.warmup, dist, pairs=args.pairs, device=device,
-                        want_e2e=not args.no_e2e)
+                        want_e2e=not args.no_e2e,
+                        check_frames=(0, n_pairs // 2 - 1, n_pairs - 1) if want_parity else ())
     clocks = sampler.stop() if rank == 0 else {}
     # total shards = world * pairs (weak scaling)
     value = main["value"] * world
@@ -464,12 +552,44 @@ def run_gpu(args) -> dict:
                      "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                      "algorithmic_bytes_per_launch": main["bytes_per_step"],
                      "source_touched_fraction": main["touched_fraction"], "kernel": "vr180::tiled::k_warp_tiled (1 launch per step)"},
-        "e2e": ({**main["e2e"], "value": main["e2e"]["value"] * world, "per_gpu_value": main["e2e"]["value"],
-                 "h2d_bytes_per_step": main["e2e"]["h2d_bytes_per_step"] * world,
-                 "d2h_bytes_per_step": main["e2e"]["d2h_bytes_per_step"] * world}
-                if main.get("e2e") else None),
+        "e2e": None,
         "clocks": clocks,
     }
+    if main.get("e2e"):
+        e = dict(main["e2e"])
+        ceiling, py = e["copy_ceiling"], main["e2e_python_api"]["value"]
+        if dist is not None:  # whole-job numbers: every rank ran its own pipeline / copy test at the same time
+            tt = torch.tensor([ceiling, py], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            ceiling, py = float(tt[0].item()), float(tt[1].item())
+        e.update({"per_gpu_value": e["value"], "value": e["value"] * world, "copy_ceiling": ceiling,
+                  "frac_of_ceiling": e["value"] * world / ceiling,
+                  "h2d_bytes_per_step": e["h2d_bytes_per_step"] * world, "d2h_bytes_per_step": e["d2h_bytes_per_step"] * world})
+        line["e2e"] = e
+        line["e2e_python_api"] = {**main["e2e_python_api"], "per_gpu_value": main["e2e_python_api"]["value"], "value": py,
+                                  "h2d_bytes_per_step": e["h2d_bytes_per_step"], "d2h_bytes_per_step": e["d2h_bytes_per_step"]}
+
+    def parity_of(w, res):
+        """Frames of the timed launch (and frame 0 of the two host-buffer legs) against cv2.remap on the oracle's maps."""
+        out = {"vs": "cv2.remap + np.concatenate on the maps of oracle/chain_np.py (the reference's get_map restated)",
+               "frames_of_the_timed_launch": [], "mismatched_bytes": 0}
+        want0 = None
+        for f, l, r, o in res.get("samples", []):
+            want = oracle_sbs(w, l, r)
+            if f == 0:
+                want0 = want
+            out["frames_of_the_timed_launch"].append(f)
+            out["mismatched_bytes"] += int((want != o).sum())
+        for key in ("e2e_frame0", "e2e_python_frame0"):
+            if key in res and want0 is not None:
+                out[key + "_mismatched_bytes"] = int((want0 != res[key]).sum())
+        out["bit_exact"] = all(v == 0 for k, v in out.items() if k.endswith("mismatched_bytes"))
+        return out
+
+    if want_parity:
+        line["parity"] = parity_of(wl, main)
+        if not line["parity"]["bit_exact"]:
+            print("PARITY FAILURE: the timed launch differs from the oracle", line["parity"], file=sys.stderr)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         step, t_maps, threads = cpu_reference_setup(wl, 2 if wl["n"] >= 4096 else 4)
         sp = 2 if wl["n"] >= 4096 else 4
@@ -489,15 +609,28 @@ def run_gpu(args) -> dict:
             "map_build_s": t_maps,
             "value_incl_map_build_for_step_batch":
                 main["pairs"] * n * 2 * n / 1e6 / (t_maps + main["pairs"] * dt / sp)}
-    if args.all_workloads and world == 1:
+    for k in ("samples", "e2e_frame0", "e2e_python_frame0"):
+        main.pop(k, None)
+    if not args.no_other_workloads and world == 1 and args.pairs is None:
+        # every other BASELINE config, 5 timed steps each, frames 0 and last of each timed launch checked like above
         others = {}
         for name, w in WORKLOADS.items():
             if name == args.workload:
                 continue
-            r = run_workload(torch, V, name, w, max(3, args.steps // 2), 3, None, want_e2e=False, device=device)
+            vary = w.get("vary", False)
+            r = run_workload(torch, V, name, w, 5, 3, None, want_e2e=False, device=device,
+                             check_frames=((0,) if vary else (0, w["pairs"] - 1)) if want_parity else ())
             a = r["bytes_per_step"] / (r["ms_per_step"] / 1e3) / 1e9
-            others[name] = {"value": r["value"], "unit": "Mpix/s", "ms_per_step": r["ms_per_step"],
-                            "pairs_per_step": r["pairs"], "roofline_frac": a / peak, "achieved_gbs": a}
+            others[name] = {"value": r["value"], "unit": "Mpix/s", "ms_per_step": r["ms_per_step"], "steps": 5,
+                            "pairs_per_step": r["pairs"], "roofline_frac": a / peak, "achieved_gbs": a,
+                            "description": w["desc"]}
+            if want_parity:
+                par = parity_of(w, r)
+                others[name]["parity_bit_exact"] = par["bit_exact"]
+                others[name]["parity_frames"] = par["frames_of_the_timed_launch"]
+                if not par["bit_exact"]:
+                    print(f"PARITY FAILURE in {name}", par, file=sys.stderr)
+            del r
         line["other_workloads"] = others
     line["gpu_launches_total_in_process"] = lib.vr180_launch_count() - launches0
     if dist is not None:
@@ -514,7 +647,8 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="8k_rot_poly_linear", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=None, help="stereo pairs per GPU per step")
-    ap.add_argument("--all-workloads", action="store_true", help="also time the other BASELINE configs (N=1)")
+    ap.add_argument("--all-workloads", action="store_true", help="(default at N=1; kept for old command lines)")
+    ap.add_argument("--no-other-workloads", action="store_true", help="only the headline workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()

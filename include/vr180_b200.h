@@ -286,6 +286,9 @@ int vr180_debug_weight_table(int K, int16_t* out);
    refills, mbarrier phase flips) with small outputs; what 1: tiled-kernel experiment flags (-1 = environment
    variable VR180_TILED_DEBUG).  Returns the previous value. */
 int vr180_debug_set(int what, int value);
+/* Copy-only ceiling of the host-buffer pipeline (bench.py e2e.copy_ceiling): page-locked host <-> device copies of
+   `bytes` each way, `reps` times, no kernel: out_gbs[4] = {H2D alone, D2H alone, H2D and D2H while both run}. */
+int vr180_debug_copy_ceiling(int device, size_t bytes, int reps, double* out_gbs);
 
 #ifdef __cplusplus
 }

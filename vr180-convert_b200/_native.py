@@ -93,6 +93,7 @@ SYMBOLS = {
     "vr180_ctx_run": (C.c_int, [C.c_void_p, C.POINTER(HostJob)]),
     "vr180_debug_weight_table": (C.c_int, [C.c_int, C.c_void_p]),
     "vr180_debug_set": (C.c_int, [C.c_int, C.c_int]),
+    "vr180_debug_copy_ceiling": (C.c_int, [C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -603,4 +603,69 @@ int vr180_ctx_run(vr180_ctx_t* c, const vr180_host_job_t* job) {
     return VR180_OK;
 }
 
+/* Measurement utility for bench.py's e2e.copy_ceiling: page-locked host <-> device copies of `bytes` each way with NO
+   kernel in between -- upload alone, download alone, and both at once on two streams (what the pipeline above
+   overlaps).  out_gbs[0..3] = {H2D alone, D2H alone, H2D while both run, D2H while both run} in GB/s (1e9). */
+int vr180_debug_copy_ceiling(int device, size_t bytes, int reps, double* out_gbs) {
+    if (!out_gbs || bytes == 0 || reps < 1) return VR180_ERR_INVALID_ARG;
+    DeviceGuard g(device);
+    if (!g.ok) return VR180_ERR_CUDA;
+    void *h_up = nullptr, *h_down = nullptr, *d_up = nullptr, *d_down = nullptr;
+    cudaStream_t s0 = nullptr, s1 = nullptr;
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    auto body = [&]() -> int {
+        VR180_CUDA(cudaHostAlloc(&h_up, bytes, cudaHostAllocPortable));
+        VR180_CUDA(cudaHostAlloc(&h_down, bytes, cudaHostAllocPortable));
+        memset(h_up, 1, bytes);
+        memset(h_down, 2, bytes);
+        VR180_CUDA(cudaMalloc(&d_up, bytes));
+        VR180_CUDA(cudaMalloc(&d_down, bytes));
+        VR180_CUDA(cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking));
+        VR180_CUDA(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
+        for (auto& ev : e) VR180_CUDA(cudaEventCreate(&ev));
+        auto timed = [&](bool up, bool down, float* ms_up, float* ms_down) -> int {
+            for (int warm = 0; warm < 2; ++warm) {
+                if (warm == 1) {
+                    if (up) VR180_CUDA(cudaEventRecord(e[0], s0));
+                    if (down) VR180_CUDA(cudaEventRecord(e[2], s1));
+                }
+                for (int r = 0; r < (warm ? reps : 1); ++r) {
+                    if (up) VR180_CUDA(cudaMemcpyAsync(d_up, h_up, bytes, cudaMemcpyHostToDevice, s0));
+                    if (down) VR180_CUDA(cudaMemcpyAsync(h_down, d_down, bytes, cudaMemcpyDeviceToHost, s1));
+                }
+                if (warm == 1) {
+                    if (up) VR180_CUDA(cudaEventRecord(e[1], s0));
+                    if (down) VR180_CUDA(cudaEventRecord(e[3], s1));
+                }
+                VR180_CUDA(cudaStreamSynchronize(s0));
+                VR180_CUDA(cudaStreamSynchronize(s1));
+            }
+            if (up) VR180_CUDA(cudaEventElapsedTime(ms_up, e[0], e[1]));
+            if (down) VR180_CUDA(cudaEventElapsedTime(ms_down, e[2], e[3]));
+            return VR180_OK;
+        };
+        float a = 0, b = 0, cu = 0, cd = 0, dummy = 0;
+        int rc;
+        if ((rc = timed(true, false, &a, &dummy)) != VR180_OK) return rc;
+        if ((rc = timed(false, true, &dummy, &b)) != VR180_OK) return rc;
+        if ((rc = timed(true, true, &cu, &cd)) != VR180_OK) return rc;
+        const double gb = (double)bytes * reps / 1e9;
+        out_gbs[0] = gb / (a / 1e3);
+        out_gbs[1] = gb / (b / 1e3);
+        out_gbs[2] = gb / (cu / 1e3);
+        out_gbs[3] = gb / (cd / 1e3);
+        return VR180_OK;
+    };
+    const int rc = body();
+    for (auto& ev : e)
+        if (ev) cudaEventDestroy(ev);
+    if (s0) cudaStreamDestroy(s0);
+    if (s1) cudaStreamDestroy(s1);
+    if (d_up) cudaFree(d_up);
+    if (d_down) cudaFree(d_down);
+    if (h_up) cudaFreeHost(h_up);
+    if (h_down) cudaFreeHost(h_down);
+    return rc;
+}
+
 }  // extern "C"
