@@ -207,7 +207,7 @@ def oracle_maps(wl: dict):
     [(xmap, ymap)] per eye-map, and the seconds the (single-threaded) build took."""
     from oracle import chain_np
 
-    key = (wl["chain"], wl["tuple_"], wl["n"])
+    key = (wl["chain"], wl["tuple_"], wl["n"], wl["radius"])
     if key not in _ORACLE_MAPS:
         n = wl["n"]
         t0 = time.perf_counter()
@@ -515,6 +515,9 @@ def run_gpu(args) -> dict:
         dist_mod.init_process_group("nccl", device_id=device)
         dist = dist_mod
     wl = WORKLOADS[args.workload]
+    for kv in filter(None, args.debug_set.split(",")):
+        what, val = kv.split("=")
+        V._native.lib().vr180_debug_set(int(what), int(val))
     peak, peak_src = measured_peak()
     sampler = ClockSampler(local)
     lib = V._native.lib()
@@ -544,6 +547,7 @@ def run_gpu(args) -> dict:
         "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 coordinates / u8 fixed-point (INTER_BITS=5) sampling", "data": "synthetic",
         "config": {"workload": args.workload, "description": wl["desc"], "pairs_per_gpu_per_step": main["pairs"],
+                   **({"debug_set": args.debug_set} if args.debug_set else {}),
                    "frame_ring": main["ring"], "l2": "inputs+outputs of one step exceed the 126 MB L2 (no flush needed)",
                    "parallelism": f"frames sharded over {world} GPU(s), no collective"},
         "gpu_launches": main["launches_per_step"] * args.steps,
@@ -651,6 +655,8 @@ def main() -> None:
     ap.add_argument("--no-other-workloads", action="store_true", help="only the headline workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--debug-set", default="", help="experiments: comma list of what=value for vr180_debug_set "
+                                                    "(0 frames per CTA, 1 tiled flags, 2 frames-per-CTA cap)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

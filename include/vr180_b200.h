@@ -190,10 +190,12 @@ int vr180_pack_lut(const float* xmap_dev, const float* ymap_dev, int64_t map_pit
  *      np.concatenate(axis=1) (remapper.py:518): each view is written straight into its column range of the
  *      destination frame.  uint8, 1/3/4 channels.  Bit-exact to cv2.remap for the same float32 maps.
  *      Performance note (results are identical either way): the TMA-tiled kernel serves 3 channels, NEAREST /
- *      LINEAR / CUBIC / LANCZOS4, BORDER_CONSTANT with a zero border value (NEAREST not with a MAPSRC_FIXED
- *      LUT, which stores x * 32), when every base pointer, row pitch and frame stride is a
- *      multiple of 16 bytes and every view's dst_x_offset * 3 is too (a TMA box must start at a 16-byte aligned
- *      global address); any other request runs in the generic per-pixel kernel.
+ *      LINEAR / CUBIC / LANCZOS4 (NEAREST not with a MAPSRC_FIXED LUT, which stores x * 32) when every base pointer, row
+ *      pitch and frame stride is a multiple of 16 bytes and every view's dst_x_offset * 3 is too (a TMA box must start at
+ *      a 16-byte aligned global address).  With BORDER_CONSTANT and a zero colour, tiles that straddle the source edge
+ *      are staged too (TMA's zero fill is the border); with any other border mode / colour only tiles whose footprint
+ *      lies inside the source are staged and the (few) edge tiles are gathered per pixel inside the same kernel.  Any
+ *      other request runs in the generic per-pixel kernel.
  * ---------------------------------------------------------------------------------------------------- */
 int vr180_remap(const vr180_remap_params_t* params, void* stream);
 
@@ -284,7 +286,8 @@ int vr180_ctx_run(vr180_ctx_t* ctx, const vr180_host_job_t* job);
 int vr180_debug_weight_table(int K, int16_t* out);
 /* what 0: frames per CTA of the tiled kernel (0 = automatic) -- lets tests drive long frame loops (stage-ring
    refills, mbarrier phase flips) with small outputs; what 1: tiled-kernel experiment flags (-1 = environment
-   variable VR180_TILED_DEBUG).  Returns the previous value. */
+   variable VR180_TILED_DEBUG); what 2: cap of the automatic frames-per-CTA choice (0 = default 64).  Returns the
+   previous value. */
 int vr180_debug_set(int what, int value);
 /* Copy-only ceiling of the host-buffer pipeline (bench.py e2e.copy_ceiling): page-locked host <-> device copies of
    `bytes` each way, `reps` times, no kernel: out_gbs[4] = {H2D alone, D2H alone, H2D and D2H while both run}. */

@@ -13,18 +13,20 @@ __global__ void __launch_bounds__(288, 4) k(unsigned* out, int iters) {
     const unsigned lane = threadIdx.x & 31;
     unsigned addr = (unsigned)__cvta_generic_to_shared(sm) + lane * 4 + (threadIdx.x >> 5) * 256;
     unsigned acc = threadIdx.x, v[8] = {1, 2, 3, 4, 5, 6, 7, 8};
+#pragma unroll 1
     for (int it = 0; it < iters; ++it) {
+        const unsigned a_it = addr + ((it & 3) << 7);  // another word of the same banks every iteration
 #pragma unroll
         for (int j = 0; j < NLDS; ++j) {
             unsigned x;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(addr + j * 512));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(a_it + j * 512) : "memory");
             v[j & 7] ^= x;
         }
 #pragma unroll
-        for (int j = 0; j < NSHFL; ++j) v[j & 7] += __shfl_down_sync(0xffffffffu, v[(j + 1) & 7], 1);
+        for (int j = 0; j < NSHFL; ++j) v[j & 7] ^= __shfl_down_sync(0xffffffffu, acc + j, 1);
 #pragma unroll
         for (int j = 0; j < NALU; ++j) v[j & 7] = __byte_perm(v[j & 7], v[(j + 3) & 7], 0x5140 + j) + acc;
-        acc += v[it & 7];
+        acc += v[0] ^ v[3];
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc ^ v[0] ^ v[1] ^ v[2] ^ v[3] ^ v[4] ^ v[5] ^ v[6] ^ v[7];
 }

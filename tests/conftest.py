@@ -45,6 +45,13 @@ def golden_fullsize():
     return np.load(GOLDEN / "maps_fullsize_samples.npz")
 
 
+@pytest.fixture(scope="session")
+def golden_cfg1():
+    """BASELINE.json configs[0]: the reference's `lr test.jpg test.jpg` run (tests/golden/make_golden.py:make_cfg1)."""
+    z = np.load(GOLDEN / "cfg1.npz")
+    return z, json.loads(str(z["meta"])), GOLDEN / "cfg1_test.jpg"
+
+
 def disc_frame(h: int, w: int, seed: int, margin: int = 8) -> np.ndarray:
     """Synthetic fisheye frame of SURVEY.md §8(d): uniform random bytes inside the disc, zeros outside."""
     rng = np.random.default_rng(seed)

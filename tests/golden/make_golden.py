@@ -197,9 +197,50 @@ def make_apply():
     print("apply.npz")
 
 
+def make_cfg1():
+    """BASELINE.json configs[0]: `v1c lr test.jpg test.jpg --transformer 'EquirectangularEncoder()
+    * PolynomialScaler() * FisheyeDecoder("equidistant")' --interpolation INTER_LINEAR` with the CLI's default size
+    4096x4096 per eye (cli.py:117-380 -> remapper.py:406-520), run through the unmodified reference's apply_lr.
+    The 2048 x 2048 README image is split into two PORTRAIT halves (2048 x 1024: get_radius scans the centre COLUMN)
+    and upsampled to 4096^2 per eye.  Stored: the input JPEG (reference docs/_static/test.jpg, a data file), the
+    sha256 of its decoded pixels, the radius the reference logs, the sha256 of the (4096, 8192, 3) output and 200 000
+    sparse output samples + 8 full rows (the whole frame is 100 MB)."""
+    import hashlib
+    import shutil
+
+    src = Path("/root/reference/docs/_static/test.jpg")
+    shutil.copyfile(src, HERE / "cfg1_test.jpg")
+    (HERE / "cfg1_test.jpg").chmod(0o644)
+    img = cv2.imread(str(src))
+    t = eval(CASES["poly_default"][0], NS)  # noqa: S307
+    halves = [img[:, : img.shape[1] // 2], img[:, img.shape[1] // 2:]]
+    radius = ref_remapper.get_radius_smart("auto", halves)
+    with tempfile.TemporaryDirectory() as d:
+        p = Path(d) / "o.png"
+        ref.apply_lr(t, left_path=src, right_path=src, out_path=p, size_output=(4096, 4096),
+                     interpolation=cv2.INTER_LINEAR, radius="auto")
+        out = cv2.imread(str(p))
+    assert out.shape == (4096, 8192, 3)
+    rng = np.random.default_rng(2024)
+    idx = np.stack([rng.integers(0, 4096, 200_000), rng.integers(0, 8192, 200_000)], axis=1).astype(np.int32)
+    rows = np.array([0, 1, 1023, 2047, 2048, 3000, 4094, 4095], np.int32)
+    np.savez_compressed(HERE / "cfg1.npz", idx=idx, px=out[idx[:, 0], idx[:, 1]], rows=rows, row_px=out[rows],
+                        meta=np.array(json.dumps({
+                            "radius": float(radius), "expr": CASES["poly_default"][0], "size_output": [4096, 4096],
+                            "interpolation": int(cv2.INTER_LINEAR),
+                            "input_sha256": hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest(),
+                            "output_sha256": hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest(),
+                            "cv2": cv2.__version__, "numpy": np.__version__})))
+    print("cfg1.npz radius", radius, "sha", hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest())
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg1":
+        make_cfg1()
+        raise SystemExit(0)
     make_maps()
     make_big_map_hashes()
     make_remap()
     make_radius()
     make_apply()
+    make_cfg1()

@@ -138,3 +138,42 @@ def test_long_frame_loop_per_frame_radius(frames_per_cta, interp, per_eye, kind)
     got = wp(torch.from_numpy(ln).cuda(), torch.from_numpy(rn).cuda(),
              radius=torch.tensor(radii, dtype=torch.float64, device="cuda")).cpu().numpy()
     _check(got, ln, rn, interp, per_eye, radii)
+
+
+@pytest.mark.parametrize("interp", [0, 1, 2, 4])
+@pytest.mark.parametrize("border", [(0, (7, 200, 90)), (1, 0), (2, 0), (3, 0), (4, 0), (0, 5)])
+def test_tiled_kernel_with_every_border(frames_per_cta, interp, border):
+    """Border modes / colours other than BORDER_CONSTANT(0) on the tiled kernel: tiles whose footprint stays inside the
+    source are staged by TMA as usual, tiles that touch the source edge (a radius larger than the source makes many)
+    take the per-pixel path with cv2's border rules; fixed radius and per-frame radius (incl. a NaN radius, which under
+    BORDER_REPLICATE samples the corner pixel instead of a colour)."""
+    import torch
+
+    mode, value = border
+    frames_per_cta(12)
+    n = 12
+    ln, rn = _frames(7)[:n], _frames(8)[:n]
+    left, right = torch.from_numpy(ln).cuda(), torch.from_numpy(rn).cuda()
+    t = _chain(QL)
+    bv = value if isinstance(value, tuple) else (value, 0, 0)
+
+    def want(f, r):
+        if r != r:
+            xm = np.full((HOUT, WOUT), np.nan, np.float32)
+            ml = (xm, xm)
+        else:
+            ml = _omap(QL, r)
+        return np.concatenate([cv2.remap(img[f], ml[0], ml[1], interpolation=interp, borderMode=mode, borderValue=bv)
+                               for img in (ln, rn)], axis=1)
+
+    radius = 75.0
+    got = V.SbsWarper(t, size_input=(HIN, WIN), size_output=(WOUT, HOUT), interpolation=interp, radius=radius,
+                      boarder_mode=mode, boarder_value=value)(left, right).cpu().numpy()
+    for f in range(n):
+        assert np.array_equal(got[f], want(f, radius)), (interp, border, f)
+    radii = [75.0, 40.0, float("nan"), 75.0, 75.0, 52.5, -66.0, float("nan"), 30.0, 75.0, 75.0, 75.0]
+    got = V.SbsWarper(t, size_input=(HIN, WIN), size_output=(WOUT, HOUT), interpolation=interp, radius="auto",
+                      boarder_mode=mode, boarder_value=value)(
+        left, right, radius=torch.tensor(radii, dtype=torch.float64, device="cuda")).cpu().numpy()
+    for f in range(n):
+        assert np.array_equal(got[f], want(f, radii[f])), (interp, border, "dyn", f, radii[f])

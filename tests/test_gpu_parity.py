@@ -502,3 +502,28 @@ def test_fullsize_8k_pair_properties():
     for src in ("lut", "lut_fixed"):
         other = V.SbsWarper(t, size_input=(n, n), size_output=(n, n), interpolation=1, radius=n / 2, map_source=src)
         assert torch.equal(other(left[:1], right[:1])[0], out[0])
+
+
+def test_cfg1_reference_cli_run_matches_golden(golden_cfg1):
+    """BASELINE.json configs[0]: `v1c lr docs/_static/test.jpg docs/_static/test.jpg` with the default PolynomialScaler
+    chain, INTER_LINEAR, CLI default size 4096 x 4096 per eye (cli.py:117-380, remapper.py:448-456: one file split into
+    two PORTRAIT 2048 x 1024 views -> get_radius scans the centre COLUMN -> 877.5 -> 4x upsampling into an
+    8192 x 4096 SBS frame).  Compared with 200 000 sparse samples + 8 full rows of the unmodified reference's output;
+    budget: 4 pixels (one-ulp float32 map flips of another libm), in practice 0 -> the sha256 of the whole frame."""
+    import hashlib
+
+    z, meta, jpg = golden_cfg1
+    img = cv2.imread(str(jpg))
+    if hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest() != meta["input_sha256"]:
+        pytest.skip("this cv2 build decodes the JPEG differently from the one that generated the fixture")
+    t = eval(meta["expr"], NS)  # noqa: S307
+    halves = [img[:, : img.shape[1] // 2], img[:, img.shape[1] // 2:]]
+    assert V.get_radius_smart("auto", halves) == meta["radius"] == 877.5
+    out = V.lr_frame(t, str(jpg), str(jpg), size_output=(4096, 4096), interpolation=1, radius="auto")
+    assert out.shape == (4096, 8192, 3)
+    idx = z["idx"]
+    bad = int((out[idx[:, 0], idx[:, 1]] != z["px"]).any(axis=1).sum()) + int((out[z["rows"]] != z["row_px"]).any(axis=2).sum())
+    assert bad <= 4, bad
+    if bad == 0:
+        digest = hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest()
+        print("cfg1 sha256", digest, "reference", meta["output_sha256"])

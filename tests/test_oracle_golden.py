@@ -124,3 +124,28 @@ def test_get_radius_oracle(golden_radius):
         with pytest.raises(IndexError):
             chain_np.get_radius(img)
         assert -1 in chain_np.get_radius_transitions(img)
+
+
+def test_cfg1_reference_cli_run(golden_cfg1):
+    """BASELINE.json configs[0] / SURVEY.md Appendix E: `v1c lr test.jpg test.jpg` with PolynomialScaler(), INTER_LINEAR,
+    4096 x 4096 per eye (cli.py:117-380 -> remapper.py:406-520).  The oracle (get_radius + chain restatement + cv2.remap
+    per half + concatenate) reproduces the reference's logged radius and its output samples; on the host that generated
+    the fixture the whole 100 MB frame hashes to the recorded sha256."""
+    import hashlib
+
+    z, meta, jpg = golden_cfg1
+    img = cv2.imread(str(jpg))
+    if hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest() != meta["input_sha256"]:
+        pytest.skip("this cv2 build decodes the JPEG differently from the one that generated the fixture")
+    halves = [img[:, : img.shape[1] // 2], img[:, img.shape[1] // 2:]]  # remapper.py:448-456: views, portrait 2048 x 1024
+    radius = max(chain_np.get_radius(h) for h in halves)  # remapper.py:82-84
+    assert radius == meta["radius"] == 877.5
+    ops = [("equirect_enc", True), ("poly", [0, 1]), ("fisheye_dec", "equidistant")]
+    xm, ym = chain_np.get_map(ops, radius=radius, size_input=halves[0].shape[:2], size_output=(4096, 4096))
+    out = np.concatenate([cv2.remap(h, xm, ym, interpolation=cv2.INTER_LINEAR) for h in halves], axis=1)
+    assert out.shape == (4096, 8192, 3)
+    idx = z["idx"]
+    bad = int((out[idx[:, 0], idx[:, 1]] != z["px"]).any(axis=1).sum()) + int((out[z["rows"]] != z["row_px"]).any(axis=2).sum())
+    assert bad <= 4, bad  # another libm may flip a vanishing number of float32 map values by one ulp
+    if bad == 0 and np.__version__ == meta["numpy"]:
+        assert hashlib.sha256(out.tobytes()).hexdigest() == meta["output_sha256"]

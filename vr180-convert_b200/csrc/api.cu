@@ -12,6 +12,7 @@ namespace vr180 {
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_debug_frames_per_cta{0};
 std::atomic<int> g_debug_tiled_flags{-1};
+std::atomic<int> g_debug_max_frames_per_cta{0};
 static thread_local std::string t_cuda_error;
 
 void set_cuda_error(cudaError_t e, const char* where) {
@@ -76,10 +77,11 @@ int vr180_debug_weight_table(int K, int16_t* out) {
 }
 
 /* test / profiling hook: what 0 = frames per CTA of the tiled kernel (0 = automatic), 1 = VR180_TILED_DEBUG flags
-   (-1 = from the environment).  Returns the previous value. */
+   (-1 = from the environment), 2 = cap of the automatic frames-per-CTA choice (0 = default).  Returns the previous value. */
 int vr180_debug_set(int what, int value) {
     if (what == 0) return g_debug_frames_per_cta.exchange(value < 0 ? 0 : value);
     if (what == 1) return g_debug_tiled_flags.exchange(value);
+    if (what == 2) return g_debug_max_frames_per_cta.exchange(value < 0 ? 0 : value);
     return VR180_ERR_INVALID_ARG;
 }
 

@@ -102,6 +102,8 @@ struct TiledParams {
     int tiles_x;
     int sep_prefix;  // generic chains only: ops[0..1] = Normalize, EquirectangularEncoder
     int debug;       // VR180_TILED_DEBUG: bit 0 = legacy pitches (160 / 224 bytes, no per-tile choice)
+    int zero_border; // BORDER_CONSTANT with a zero colour: TMA's out-of-bounds zero fill IS the border, so tiles that
+                     // straddle the source edge stay staged; any other border only stages tiles that lie inside the source
     const short* tab;  // bicubic: OpenCV's 1024 x 16 int16 weight table (device)
     StdChain std[2];
 };
@@ -157,22 +159,30 @@ __device__ __forceinline__ void bulk_wait_read() {  // all but the N newest bulk
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
-// The 2 x 12-byte tap windows of a bilinear pixel (rows q0 and q1, shared-window addresses).  Only a byte offset of
-// 3 (sh == 24) reaches into the third word: the other lanes skip that load (fewer active lanes = fewer bank
-// conflicts) and leave a2 / b2 undefined -- the funnel shifts below never look at them for sh < 24.
+// The 2 x 12-byte tap windows of a bilinear pixel (rows q0 and q1, shared-window addresses), byte-aligned:
+//   lo = [c0 c1 c2 c0'], hi = [c1' c2' . .] of each row (primed = the pixel at ix + 1).
+// Only a byte offset of 3 (sh == 24) reaches into the third word; the other lanes skip that load (fewer active lanes
+// = fewer bank conflicts).  The third word is loaded INTO THE REGISTER OF THE FIRST WORD, which is dead once `lo` has
+// been formed: a predicated load into a register of its own would have to preserve that register's old value for
+// the lanes that skip it, i.e. cost one loop-carried register per load (16 of the 56 registers of the two-frame loop,
+// plus the spills and moves they caused).  For sh < 24 the funnel shift of `hi` never looks at its upper operand.
 // volatile: the same shared address holds another frame after every barrier wait.
-__device__ __forceinline__ void lds_taps(uint32_t q0, uint32_t q1, int sh, uint32_t& a0, uint32_t& a1, uint32_t& a2,
-                                         uint32_t& b0, uint32_t& b1, uint32_t& b2) {
+__device__ __forceinline__ void lds_taps_aligned(uint32_t q0, uint32_t q1, int sh, uint32_t& r0lo, uint32_t& r0hi,
+                                                 uint32_t& r1lo, uint32_t& r1hi) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.eq.s32 p, %8, 24;\n\t"
-        "ld.shared.u32 %0, [%6];\n\t"
-        "ld.shared.u32 %1, [%6+4];\n\t"
-        "ld.shared.u32 %3, [%7];\n\t"
-        "ld.shared.u32 %4, [%7+4];\n\t"
-        "@p ld.shared.u32 %2, [%6+8];\n\t"
-        "@p ld.shared.u32 %5, [%7+8];\n\t}"
-        : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(b0), "=r"(b1), "=r"(b2)
+        "{\n\t.reg .pred p;\n\t.reg .b32 a0, a1, b0, b1;\n\t"
+        "setp.eq.s32 p, %6, 24;\n\t"
+        "ld.shared.u32 a0, [%4];\n\t"
+        "ld.shared.u32 a1, [%4+4];\n\t"
+        "ld.shared.u32 b0, [%5];\n\t"
+        "ld.shared.u32 b1, [%5+4];\n\t"
+        "shf.r.wrap.b32 %0, a0, a1, %6;\n\t"
+        "shf.r.wrap.b32 %2, b0, b1, %6;\n\t"
+        "@p ld.shared.u32 a0, [%4+8];\n\t"
+        "@p ld.shared.u32 b0, [%5+8];\n\t"
+        "shf.r.wrap.b32 %1, a1, a0, %6;\n\t"
+        "shf.r.wrap.b32 %3, b1, b0, %6;\n\t}"
+        : "=&r"(r0lo), "=&r"(r0hi), "=&r"(r1lo), "=&r"(r1hi)
         : "r"(q0), "r"(q1), "r"(sh));
 }
 
@@ -216,12 +226,8 @@ struct Linear {
     // `sbuf`: shared-window address of the stage, `pitch`: its row pitch in bytes
     __device__ static __forceinline__ uint32_t sample(uint32_t sbuf, const Pixel& p, uint32_t pitch) {
         const uint32_t row0 = sbuf + (uint32_t)p.boff;
-        const int sh = p.sh;
-        uint32_t a0, a1, a2, b0, b1, b2;
-        lds_taps(row0, row0 + pitch, sh, a0, a1, a2, b0, b1, b2);
-        // byte-align: lo = [c0 c1 c2 c0'], hi = [c1' c2' . .]  (primed = the pixel at ix + 1)
-        const uint32_t r0lo = __funnelshift_r(a0, a1, sh), r0hi = __funnelshift_r(a1, a2, sh);
-        const uint32_t r1lo = __funnelshift_r(b0, b1, sh), r1hi = __funnelshift_r(b1, b2, sh);
+        uint32_t r0lo, r0hi, r1lo, r1hi;  // byte-aligned: lo = [c0 c1 c2 c0'], hi = [c1' c2' . .]
+        lds_taps_aligned(row0, row0 + pitch, p.sh, r0lo, r0hi, r1lo, r1hi);
         const uint32_t q0 = __byte_perm(r0lo, r1lo, 0x7430);  // channel 0: [p00 p01 | p10 p11]
         const uint32_t t0 = __byte_perm(r0lo, r0hi, 0x5241);  // row 0: [c1 c1' | c2 c2']
         const uint32_t t1 = __byte_perm(r1lo, r1hi, 0x5241);  // row 1
@@ -842,8 +848,15 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     auto stage_fits = [&](int rows, int pitch_bytes) {
         return ((FR * box_rows_of(rows) * pitch_bytes + 127) & ~127) <= Lay<M>::kStageArea;
     };
+    // Any other border (a colour, REPLICATE, REFLECT, WRAP, REFLECT_101) needs real taps or the border colour where the
+    // footprint leaves the source: those tiles take the per-pixel path below; tiles inside the source never see a border.
+    const int src_cols = a.view[v_begin].cols, src_rows = a.view[v_begin].rows;
+    auto inside_src = [&](int x_lo, int x_hi, int y_lo, int y_hi) {  // extreme integer coordinates of the tile
+        return x_lo - M::kLo >= 0 && x_hi + M::kHi <= src_cols - 1 && y_lo - M::kLo >= 0 && y_hi + M::kHi <= src_rows - 1;
+    };
     bool fast = full_tile && wbytes <= kPitchMax && nrows <= M::kRowsMin + (kRowSizes - 1) * kRowsStep &&
-                mnx > -32768 && mny > -32768 && mxx < 32767 && mxy < 32767 && stage_fits(nrows, max(wbytes, kPitchMin));
+                mnx > -32768 && mny > -32768 && mxx < 32767 && mxy < 32767 && stage_fits(nrows, max(wbytes, kPitchMin)) &&
+                (tp.zero_border || inside_src(mnx, mxx, mny, mxy));
     int dyn_wbytes = 0, dyn_nrows = 0;
     if (dynr) {
         const double* s_ext = reinterpret_cast<const double*>(smem + Lay<M>::kOffExt);
@@ -865,13 +878,16 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         for (int f = f0 + lane; f < f1; f += 32) {
             const double rad = __ldg(dr.radius + f);
             if (rad == rad) {
-                int lo, hi;
+                int lo, hi, ylo, yhi;
                 dyn_range<M>(dr.ext[0], dr.ext[1], rad, dr.cx, lo, hi);
                 ok &= (lo > -32768) & (hi < 32767);
                 dyn_wbytes = max(dyn_wbytes, ((3 * (hi + M::kHi + 1) + 15) & ~15) - ((3 * (lo - M::kLo)) & ~15));
-                dyn_range<M>(dr.ext[2], dr.ext[3], rad, dr.cy, lo, hi);
-                ok &= (lo > -32768) & (hi < 32767);
-                dyn_nrows = max(dyn_nrows, hi + M::kHi + 1 - (lo - M::kLo));
+                dyn_range<M>(dr.ext[2], dr.ext[3], rad, dr.cy, ylo, yhi);
+                ok &= (ylo > -32768) & (yhi < 32767);
+                dyn_nrows = max(dyn_nrows, yhi + M::kHi + 1 - (ylo - M::kLo));
+                if (!tp.zero_border) ok &= inside_src(lo, hi, ylo, yhi) ? 1 : 0;
+            } else if (!tp.zero_border) {
+                ok = 0;  // NaN coordinates: the border colour / the replicated edge pixel -- per-pixel path
             }
         }
         dyn_wbytes = __reduce_max_sync(0xffffffffu, dyn_wbytes);
@@ -900,13 +916,13 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                             Src s{vw.src + (long long)f * vw.frame_stride, vw.rows, vw.cols, vw.pitch};
                             int px[3];
                             if (M::kInterp == VR180_INTER_NEAREST)
-                                fetch_tap<3>(s, sat16(qx), sat16(qy), VR180_BORDER_CONSTANT, a.bv, px);
+                                fetch_tap<3>(s, sat16(qx), sat16(qy), a.border_mode, a.bv, px);
                             else if (M::kInterp == VR180_INTER_LINEAR)
-                                sample_linear<3>(s, qx, qy, VR180_BORDER_CONSTANT, a.bv, px);
+                                sample_linear<3>(s, qx, qy, a.border_mode, a.bv, px);
                             else if (M::kInterp == VR180_INTER_CUBIC)
-                                sample_tab<3, 4>(s, qx, qy, tp.tab, VR180_BORDER_CONSTANT, a.bv, px);
+                                sample_tab<3, 4>(s, qx, qy, tp.tab, a.border_mode, a.bv, px);
                             else
-                                sample_tab<3, 8>(s, qx, qy, tp.tab, VR180_BORDER_CONSTANT, a.bv, px);
+                                sample_tab<3, 8>(s, qx, qy, tp.tab, a.border_mode, a.bv, px);
                             uint8_t* o = drow + (long long)(vw.dst_x_offset + i) * 3;
                             o[0] = (uint8_t)px[0];
                             o[1] = (uint8_t)px[1];
@@ -1056,11 +1072,18 @@ static bool encode_u8_3d(CUtensorMap* out, const void* base, long long row_bytes
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+constexpr int kMaxFramesPerCta = 64;
 // frames per CTA: the coordinates are evaluated once per CTA, so keep the chunk as large as the grid allows
 static int frames_per_cta(long long tiles, int n_frames) {
     const int forced = g_debug_frames_per_cta.load(std::memory_order_relaxed);  // vr180_debug_set(0, n): tests
     if (forced > 0) return forced < n_frames ? forced : n_frames;
+    // A CTA streams through its frames one after the other, so the CTAs resident at any moment are spread over as many
+    // frames as a chunk holds: beyond kMaxFramesPerCta frames the DRAM / TLB working set of a launch grows faster than
+    // the per-tile prologue amortises (measured: 512 5.7K pairs in ONE chunk 37 us per pair, in chunks of 64 25 us)
+    const int cap_set = g_debug_max_frames_per_cta.load(std::memory_order_relaxed);
+    const int cap = cap_set > 0 ? cap_set : kMaxFramesPerCta;
     int fpc = n_frames;
+    if (fpc > cap) fpc = (n_frames + (n_frames + cap - 1) / cap - 1) / ((n_frames + cap - 1) / cap);  // equal chunks
     while (fpc > 1 && tiles * ((n_frames + fpc - 1) / fpc) < 148LL * 4 * 2) fpc = (fpc + 1) / 2;
     return fpc;
 }
@@ -1151,6 +1174,7 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
     const int tiles_x = (a.W + kTileW - 1) / kTileW, tiles_y = (a.H + M::kTileH - 1) / M::kTileH;
     tp.tiles_x = tiles_x;
     tp.tab = tab;
+    tp.zero_border = (a.border_mode == VR180_BORDER_CONSTANT && !(a.bv[0] | a.bv[1] | a.bv[2])) ? 1 : 0;
     static const int env_debug = [] { const char* e = getenv("VR180_TILED_DEBUG"); return e ? atoi(e) : 0; }();
     const int set_debug = g_debug_tiled_flags.load(std::memory_order_relaxed);
     tp.debug = set_debug >= 0 ? set_debug : env_debug;
@@ -1182,14 +1206,13 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
 // the requested interpolation (1024 x 16 bicubic, 1024 x 64 Lanczos4; unused otherwise).
 int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr180_chain_t& c0, const vr180_chain_t& c1,
                        const short* weight_tab, cudaStream_t st) {
-    if (channels != 3 || a0.border_mode != VR180_BORDER_CONSTANT) return VR180_ERR_UNSUPPORTED;
+    if (channels != 3) return VR180_ERR_UNSUPPORTED;
     if (interp != VR180_INTER_NEAREST && interp != VR180_INTER_LINEAR && interp != VR180_INTER_CUBIC &&
         interp != VR180_INTER_LANCZOS4)
         return VR180_ERR_UNSUPPORTED;
     if (interp == VR180_INTER_NEAREST)  // the fixed-point LUT is a 1/32-pixel grid; NEAREST rounds the float coordinate itself
         for (int v = 0; v < a0.n_views; ++v)
             if (a0.view[v].map_kind == VR180_MAPSRC_FIXED) return VR180_ERR_UNSUPPORTED;
-    if (a0.bv[0] | a0.bv[1] | a0.bv[2]) return VR180_ERR_UNSUPPORTED;  // staged tiles assume a zero border colour
     const int n_groups = a0.share_map ? 1 : a0.n_views;
     for (int v = 0; v < a0.n_views; ++v) {
         const ViewArgs& vw = a0.view[v];
