@@ -49,12 +49,17 @@ WORKLOADS = {
     "4k_pair_linear": dict(n=2048, interp=1, tuple_=False, chain="base", src="analytic", radius="fixed", pairs=1,
                            desc="single 4K pair (2x2048^2 -> 4096x2048), base chain, fused analytic, INTER_LINEAR "
                                 "[BASELINE configs[1]]; a ring of pairs larger than L2 is cycled"),
-    "5k7_lut_linear": dict(n=2880, interp=1, tuple_=False, chain="base", src="lut_fixed", radius="fixed", pairs=64,
-                           desc="batched 5.7K pairs (2x2880^2 -> 5760x2880), cached fixed-point LUT, INTER_LINEAR "
+    "5k7_lut_linear": dict(n=2880, interp=1, tuple_=False, chain="base", src="lut_packed", radius="fixed", pairs=64,
+                           desc="batched 5.7K pairs (2x2880^2 -> 5760x2880), cached tile-packed LUT (4 B/px), INTER_LINEAR "
                                 "[BASELINE configs[3]]"),
-    "5k7_lut_linear_512": dict(n=2880, interp=1, tuple_=False, chain="base", src="lut_fixed", radius="fixed", pairs=512,
-                               desc="512 resident 5.7K pairs per GPU (51 GB in + 51 GB out), cached fixed-point LUT, "
+    "5k7_lut_linear_512": dict(n=2880, interp=1, tuple_=False, chain="base", src="lut_packed", radius="fixed", pairs=512,
+                               desc="512 resident 5.7K pairs per GPU (25.5 GB in + 25.5 GB out), cached tile-packed LUT, "
                                     "INTER_LINEAR, one launch [BASELINE configs[3]: 1024 pairs over >= 2 GPUs]"),
+    "5k7_lutfixed_linear": dict(n=2880, interp=1, tuple_=False, chain="base", src="lut_fixed", radius="fixed", pairs=64,
+                                desc="as 5k7_lut_linear with the 8 B/px fixed-point LUT (int32 sx, sy)"),
+    "4k_pair_lut_linear": dict(n=2048, interp=1, tuple_=False, chain="base", src="lut_packed", radius="fixed", pairs=1,
+                               desc="single 4K pair, cached tile-packed LUT instead of the FP64 chain (the per-frame path "
+                                    "of a video loop) [BASELINE configs[1]]"),
     "8k_nearest_fixed": dict(n=4096, interp=0, tuple_=False, chain="base", src="analytic", radius="fixed", pairs=16,
                              desc="batched 8K pairs, base chain, fused analytic, INTER_NEAREST, fixed radius (the pipeline "
                                   "without the interpolation arithmetic)"),
@@ -338,7 +343,7 @@ def run_workload(torch, V, wl_name: str, wl: dict, steps: int, warmup: int, dist
     right = synth_frames_torch(torch, pairs * ring, n, 2, device, vary_margin=wl.get("vary", False))
     out = torch.empty((pairs * ring, n, 2 * n, 3), dtype=torch.uint8, device=device)
     if wl["src"] != "analytic":
-        wp.fixed_lut() if wl["src"] == "lut_fixed" else wp.maps()
+        {"lut_fixed": wp.fixed_lut, "lut_packed": wp.packed_lut, "lut": wp.maps}[wl["src"]]()
     state = {"i": 0}
 
     def step():
@@ -365,7 +370,7 @@ def run_workload(torch, V, wl_name: str, wl: dict, steps: int, warmup: int, dist
     if plan_for_maps is not wp or wl["src"] == "analytic":
         plan_for_maps._maps = None
     del maps
-    lut_bytes = {"analytic": 0, "lut": 8, "lut_fixed": 8}[wl["src"]] * n * n * (1 if not wl["tuple_"] else 2)
+    lut_bytes = {"analytic": 0, "lut": 8, "lut_fixed": 8, "lut_packed": 4}[wl["src"]] * n * n * (1 if not wl["tuple_"] else 2)
     bytes_step = pairs * (2 * n * n * 3 + 2 * frac_in * n * n * 3) + lut_bytes  # LUT is read once per launch
     res = {"ms_per_step": ms, "mpix_per_step": mpix_step, "value": mpix_step / (ms / 1e3), "pairs": pairs,
            "launches_per_step": launches_per_step, "bytes_per_step": bytes_step, "touched_fraction": frac_in,

@@ -114,12 +114,15 @@ typedef struct vr180_image {
 typedef enum vr180_map_kind {
     VR180_MAPSRC_ANALYTIC = 0, /* evaluate `chain` per output pixel in registers; no LUT is read or written */
     VR180_MAPSRC_FLOAT2 = 1,   /* planar float32 xmap / ymap, exactly what cv2.remap takes                 */
-    VR180_MAPSRC_FIXED = 2     /* int32 pairs (sx, sy) = cvRound(map*32) produced by vr180_pack_lut         */
+    VR180_MAPSRC_FIXED = 2,    /* int32 pairs (sx, sy) = cvRound(map*32) produced by vr180_pack_lut         */
+    VR180_MAPSRC_PACKED = 3    /* tile-packed 4-byte LUT from vr180_pack_lut_tiles + the float32 maps it was built
+                                  from (xmap / ymap, read only by tiles that cannot be packed)                 */
 } vr180_map_kind;
 
 typedef struct vr180_mapsrc {
     int32_t kind; /* vr180_map_kind */
-    int32_t reserved;
+    int32_t packed_interpolation; /* PACKED: the VR180_INTER_* the packed LUT was built for (tile shape and rounding
+                                     are per mode); a mismatch with the request falls back to xmap / ymap */
     const vr180_chain_t* chain; /* host pointer; ANALYTIC: full chain Normalize..Denormalize (copied at call) */
     const float* xmap;          /* FLOAT2: device, H rows of W floats, `map_pitch` elements apart            */
     const float* ymap;
@@ -130,6 +133,7 @@ typedef struct vr180_mapsrc {
        (remapper.py:379 -> :54-56).  ANALYTIC only; NULL = use the scale stored in the chain.  A NaN radius
        (get_radius found no transition) makes every coordinate NaN -> border colour. */
     const double* radius_dev;
+    const void* packed;         /* PACKED: device buffer filled by vr180_pack_lut_tiles                       */
 } vr180_mapsrc_t;
 
 /* One eye / one image stream: source frames, their coordinate source, and where the result lands. */
@@ -184,6 +188,23 @@ int vr180_build_map(const vr180_chain_t* chain, int out_w, int out_h, float* xma
  * ---------------------------------------------------------------------------------------------------- */
 int vr180_pack_lut(const float* xmap_dev, const float* ymap_dev, int64_t map_pitch, int out_w, int out_h,
                    int32_t* fixed_dev, int64_t fixed_pitch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * (2a') tile-packed LUT -- the cached-LUT form the tiled kernel reads with one 128-bit load per thread.
+ *      For every output tile of the requested interpolation (32 x 32 px NEAREST / LINEAR, 32 x 16 CUBIC, 32 x 8
+ *      LANCZOS4) it stores a 16-byte header {min ix, max ix, min iy, max iy (int16), packable flag} and one uint32
+ *      per pixel {ix - min ix : 8, iy - min iy : 8, ax : 5, ay : 5} in the order the kernel's threads consume them
+ *      (thread-major), with (ix, iy, ax, ay) exactly the integers cv::remap derives from the float32 maps
+ *      (sx = cvRound(x * 32), ix = sx >> 5, ax = sx & 31; NEAREST: ix = cvRound(x)) -- lossless w.r.t. the remap
+ *      output.  4 bytes per pixel instead of 8, and the tile's source rectangle comes from the header instead of a
+ *      block-wide reduction.  Tiles that cannot be packed (NaN / saturated coordinates, footprints wider than 255 px,
+ *      partial edge tiles) are flagged and read the float32 maps instead.  Replaces the convertMaps step inside
+ *      cv.remap at remapper.py:389 for apply()'s one-map-many-images loop (remapper.py:381-398).
+ *      vr180_packed_lut_bytes: size of the device buffer for an out_w x out_h map.
+ * ---------------------------------------------------------------------------------------------------- */
+size_t vr180_packed_lut_bytes(int out_w, int out_h, int interpolation);
+int vr180_pack_lut_tiles(const float* xmap_dev, const float* ymap_dev, int64_t map_pitch, int out_w, int out_h,
+                         int interpolation, void* packed_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * (2b) remap / fused warp + SBS packing -- replaces cv.remap per image (remapper.py:388-398) and
@@ -268,7 +289,7 @@ typedef struct vr180_host_job {
     uint8_t* const* dst_frames;
     /* Host buffers that are not page-locked (plain NumPy arrays) cannot be DMA'd asynchronously: they are packed
        into / unpacked from a pinned ring owned by the context by `copy_threads` host threads (0 = default:
-       min(8, cores / 4), or $VR180_COPY_THREADS), overlapped with the GPU work of the neighbouring chunks.
+       min(12, cores / 2), or $VR180_COPY_THREADS), overlapped with the GPU work of the neighbouring chunks.
        staging: VR180_STAGE_AUTO = per buffer, decided with cudaPointerGetAttributes; ALWAYS / NEVER force it. */
     int32_t staging;
     int32_t copy_threads;

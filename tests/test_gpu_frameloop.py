@@ -94,10 +94,11 @@ def test_long_frame_loop_fixed_radius(frames_per_cta, interp, per_eye, fpc):
     _check(got, ln, rn, interp, per_eye, [radius] * N_FRAMES)
 
 
-@pytest.mark.parametrize("src", ["lut", "lut_fixed"])
+@pytest.mark.parametrize("src", ["lut", "lut_fixed", "lut_packed"])
 @pytest.mark.parametrize("interp", [0, 1, 2, 4])
 def test_long_frame_loop_lut_sources(frames_per_cta, interp, src):
-    """The cached-LUT coordinate sources (float2 maps, fixed-point LUT) through the same long frame loop."""
+    """The cached-LUT coordinate sources (float2 maps, fixed-point LUT, tile-packed LUT) through the same long frame
+    loop."""
     import torch
 
     if src == "lut_fixed" and interp == 0:

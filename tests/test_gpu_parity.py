@@ -259,7 +259,7 @@ def test_sbs_warper_sources_agree_and_match_oracle(interp):
     left = torch.from_numpy(_frames(n, hin, win, 0)).cuda()
     right = torch.from_numpy(_frames(n, hin, win, 100)).cuda()
     outs = {}
-    for src in ("analytic", "lut", "lut_fixed"):
+    for src in ("analytic", "lut", "lut_fixed", "lut_packed"):
         if src == "lut_fixed" and interp == 0:
             continue
         wp = V.SbsWarper(t, size_input=(hin, win), size_output=(wout, hout), interpolation=interp, radius=80.0,
@@ -527,3 +527,37 @@ def test_cfg1_reference_cli_run_matches_golden(golden_cfg1):
     if bad == 0:
         digest = hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest()
         print("cfg1 sha256", digest, "reference", meta["output_sha256"])
+
+
+@pytest.mark.parametrize("interp", [0, 1, 2, 4])
+def test_packed_lut_tiles_with_unpackable_tiles(interp):
+    """vr180_pack_lut_tiles on maps that contain NaN / huge coordinates, a footprint wider than 255 px and partial edge
+    tiles: those tiles are flagged and read the float32 maps; every pixel must equal cv2.remap on the same maps."""
+    import torch
+
+    rng = np.random.default_rng(31 + interp)
+    hin, win, wout, hout = 300, 420, 208, 104  # 208 x 104: partial bottom tiles for every mode
+    src = rng.integers(0, 256, (2, hin, win, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[:hout, :wout].astype(np.float32)
+    xm = xx * 1.3 + 20 + 0.37 * np.sin(yy / 7).astype(np.float32)
+    ym = yy * 1.7 + 15 + 0.41 * np.cos(xx / 9).astype(np.float32)
+    xm[0:32, 0:32] = np.nan               # a tile of NaN coordinates
+    xm[40, 40] = 1e9                      # saturated coordinate
+    xm[32:64, 64:96] = (xx[32:64, 64:96] - 64) * 12.5   # footprint 400 px wide: cannot be packed (and not staged)
+    ym[70, 100] = -np.inf
+
+    class Maps(V.TransformerBase):  # an opaque transformer that returns these maps: the plan goes through host_maps
+        def transform(self, x, y, **kw):
+            return xm.astype(np.float64), ym.astype(np.float64)
+
+        def inverse_transform(self, x, y, **kw):
+            raise NotImplementedError
+
+    left = torch.from_numpy(src).cuda()
+    wp = V.SbsWarper(V.MultiTransformer(transformers=[Maps()]), size_input=(hin, win), size_output=(wout, hout),
+                     interpolation=interp, radius=1.0, map_source="lut_packed")
+    wp._maps = torch.from_numpy(np.stack([xm, ym])[None]).cuda()  # bypass Normalize / Denormalize: these ARE the maps
+    got = wp(left, left.flip(0)).cpu().numpy()
+    for f in range(2):
+        want = np.concatenate([cv2.remap(src[f], xm, ym, interpolation=interp), cv2.remap(src[1 - f], xm, ym, interpolation=interp)], axis=1)
+        assert np.array_equal(got[f], want), (interp, f, int((got[f] != want).sum()))

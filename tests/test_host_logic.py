@@ -37,9 +37,9 @@ def test_struct_sizes_match_header_layout():
     assert C.sizeof(N.Op) == 8 + 8 * 12
     assert C.sizeof(N.Chain) == 8 + 12 * C.sizeof(N.Op)
     assert C.sizeof(N.Image) == 40
-    assert C.sizeof(N.MapSrc) == 56
-    assert C.sizeof(N.View) == 40 + 56 + 8
-    assert C.sizeof(N.RemapParams) == 8 + 2 * 104 + 24 + 24
+    assert C.sizeof(N.MapSrc) == 64
+    assert C.sizeof(N.View) == 40 + 64 + 8
+    assert C.sizeof(N.RemapParams) == 8 + 2 * 112 + 24 + 24
 
 
 def test_ctypes_structs_match_the_c_header(tmp_path):
@@ -51,7 +51,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
                                                "copy_threads"]),
               "vr180_remap_params_t": ("RemapParams", ["view", "share_map", "border_value", "dst", "dst_frame_stride"]),
               "vr180_view_t": ("View", ["map", "dst_x_offset"]),
-              "vr180_mapsrc_t": ("MapSrc", ["chain", "fixed", "map_pitch", "radius_dev"]),
+              "vr180_mapsrc_t": ("MapSrc", ["packed_interpolation", "chain", "fixed", "map_pitch", "radius_dev", "packed"]),
               "vr180_image_t": ("Image", ["pitch", "frame_stride"]),
               "vr180_chain_t": ("Chain", ["ops"]),
               "vr180_op_t": ("Op", ["p"])}

@@ -19,7 +19,7 @@ OP_NORMALIZE, OP_DENORMALIZE, OP_DENORMALIZE_INV, OP_ZOOM, OP_ZOOM_INV = 1, 2, 3
 OP_EQUIRECT_ENC, OP_EQUIRECT_DEC, OP_FISHEYE_ENC, OP_FISHEYE_DEC = 6, 7, 8, 9
 OP_RECTILINEAR_DEC, OP_RECTILINEAR_DEC_INV, OP_POLY, OP_ROT3 = 10, 11, 12, 13
 MAPPING_CODES = {"rectilinear": 0, "stereographic": 1, "equidistant": 2, "equisolid": 3, "orthographic": 4}
-MAPSRC_ANALYTIC, MAPSRC_FLOAT2, MAPSRC_FIXED = 0, 1, 2
+MAPSRC_ANALYTIC, MAPSRC_FLOAT2, MAPSRC_FIXED, MAPSRC_PACKED = 0, 1, 2, 3
 
 
 class NativeError(RuntimeError):
@@ -40,8 +40,9 @@ class Image(C.Structure):
 
 
 class MapSrc(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("chain", C.POINTER(Chain)), ("xmap", C.c_void_p),
-                ("ymap", C.c_void_p), ("fixed", C.c_void_p), ("map_pitch", C.c_int64), ("radius_dev", C.c_void_p)]
+    _fields_ = [("kind", C.c_int32), ("packed_interpolation", C.c_int32), ("chain", C.POINTER(Chain)),
+                ("xmap", C.c_void_p), ("ymap", C.c_void_p), ("fixed", C.c_void_p), ("map_pitch", C.c_int64),
+                ("radius_dev", C.c_void_p), ("packed", C.c_void_p)]
 
 
 class View(C.Structure):
@@ -80,6 +81,9 @@ SYMBOLS = {
     "vr180_build_map": (C.c_int, [C.POINTER(Chain), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "vr180_pack_lut": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64,
                                  C.c_void_p]),
+    "vr180_packed_lut_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "vr180_pack_lut_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p]),
     "vr180_remap": (C.c_int, [C.POINTER(RemapParams), C.c_void_p]),
     "vr180_get_radius": (C.c_int, [C.POINTER(Image), C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),

@@ -104,6 +104,20 @@ int vr180_pack_lut(const float* xmap_dev, const float* ymap_dev, int64_t map_pit
     return launch_pack_lut(xmap_dev, ymap_dev, map_pitch, out_w, out_h, fixed_dev, fixed_pitch, (cudaStream_t)stream);
 }
 
+size_t vr180_packed_lut_bytes(int out_w, int out_h, int interpolation) {
+    if (out_w <= 0 || out_h <= 0) return 0;
+    return packed_lut_bytes(out_w, out_h, interpolation);
+}
+
+int vr180_pack_lut_tiles(const float* xmap_dev, const float* ymap_dev, int64_t map_pitch, int out_w, int out_h,
+                         int interpolation, void* packed_dev, void* stream) {
+    if (!xmap_dev || !ymap_dev || !packed_dev || out_w <= 0 || out_h <= 0 || map_pitch < out_w) return VR180_ERR_INVALID_ARG;
+    if (packed_lut_bytes(out_w, out_h, interpolation) == 0) return VR180_ERR_UNSUPPORTED;
+    DeviceGuard g(packed_dev);
+    if (!g.ok) return VR180_ERR_INVALID_ARG;
+    return launch_pack_lut_tiles(xmap_dev, ymap_dev, map_pitch, out_w, out_h, interpolation, packed_dev, (cudaStream_t)stream);
+}
+
 int vr180_remap(const vr180_remap_params_t* params, void* stream) {
     if (!params || !params->dst) return VR180_ERR_INVALID_ARG;
     DeviceGuard g(params->dst);

@@ -68,6 +68,7 @@ struct ViewArgs {
     long long map_pitch;
     const double* radius_dev;
     int dst_x_offset;
+    const void* packed;  // tile-packed LUT built for THIS interpolation (tiled kernel only), or nullptr
 };
 
 struct RemapArgs {
@@ -87,6 +88,9 @@ int launch_build_map(const vr180_chain_t* chain, int out_w, int out_h, float* xm
 int launch_pack_lut(const float* xmap, const float* ymap, int64_t map_pitch, int out_w, int out_h, int32_t* fixed,
                     int64_t fixed_pitch, cudaStream_t st);
 int launch_remap(const vr180_remap_params_t* p, cudaStream_t st);
+size_t packed_lut_bytes(int out_w, int out_h, int interp);  // tiled.cu; 0 = interpolation without a tiled mode
+int launch_pack_lut_tiles(const float* xmap, const float* ymap, int64_t map_pitch, int out_w, int out_h, int interp,
+                          void* packed, cudaStream_t st);
 int launch_remap_tiled(const RemapArgs& a, int channels, int interp, const vr180_chain_t& c0, const vr180_chain_t& c1,
                        const short* weight_tab, cudaStream_t st);  // tiled.cu; VR180_ERR_UNSUPPORTED = not eligible, use the generic kernel
 int launch_get_radius(const vr180_image_t* views, int n_views, int n_frames, double threshold, int32_t* transitions,

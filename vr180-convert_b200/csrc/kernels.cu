@@ -239,6 +239,11 @@ int launch_remap(const vr180_remap_params_t* p, cudaStream_t st) {
                 o.radius_dev = vw.map.radius_dev;
                 break;
             }
+            case VR180_MAPSRC_PACKED:  // the float32 maps + (tiled kernel, same interpolation only) their packed tiles
+                if (!vw.map.packed) return VR180_ERR_INVALID_ARG;
+                if (vw.map.packed_interpolation == interp) o.packed = vw.map.packed;
+                o.map_kind = VR180_MAPSRC_FLOAT2;
+                [[fallthrough]];
             case VR180_MAPSRC_FLOAT2:
                 if (!vw.map.xmap || !vw.map.ymap || vw.map.map_pitch < p->out_w) return VR180_ERR_INVALID_ARG;
                 o.xmap = vw.map.xmap;

@@ -159,8 +159,10 @@ int default_copy_threads() {
         const int n = atoi(e);
         if (n >= 1) return std::min(n, 64);
     }
+    // packing a pageable frame is a plain memcpy (~6-10 GB/s per core); the PCIe link takes ~50 GB/s each way, so a GPU
+    // needs ~8 copy threads to be fed from pageable memory.  Half the cores, at most 12.
     const unsigned hw = std::thread::hardware_concurrency();
-    return (int)std::max(2u, std::min(8u, hw / 4));
+    return (int)std::max(2u, std::min(12u, hw / 2));
 }
 
 bool is_page_locked(const void* p) {

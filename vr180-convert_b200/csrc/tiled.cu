@@ -100,6 +100,7 @@ struct StdChain {
 
 struct TiledParams {
     int tiles_x;
+    int n_tiles;     // tiles of one map (tiles_x * tiles_y): layout of a tile-packed LUT
     int sep_prefix;  // generic chains only: ops[0..1] = Normalize, EquirectangularEncoder
     int debug;       // VR180_TILED_DEBUG: bit 0 = legacy pitches (160 / 224 bytes, no per-tile choice)
     int zero_border; // BORDER_CONSTANT with a zero colour: TMA's out-of-bounds zero fill IS the border, so tiles that
@@ -113,6 +114,28 @@ struct alignas(64) TmaMaps {
     CUtensorMap src[2][kWidths][kRowSizes];  // [view][box bytes kPitchMin + 16 w][box rows kRowsMin + 8 r]: uint8 (cols * 3, rows, frames)
     CUtensorMap dst;                   // uint8 (dst_pitch, H, frames), box (96, tile height, 1)
 };
+
+// ---- tile-packed LUT (include/vr180_b200.h, vr180_pack_lut_tiles) -----------------------------------------------
+// buffer = [n_tiles x PackedHdr][pad to 256 bytes][n_tiles x (256 threads x kPx) uint32, thread-major]
+// entry  = (ix - mnx) | (iy - mny) << 8 | ax << 16 | ay << 21     (ax = ay = 0 for INTER_NEAREST)
+struct PackedHdr {
+    short mnx, mxx, mny, mxy;  // integer source coordinates of the tile: min / max of ix and iy
+    int flags;                 // bit 0: packable (full tile, finite unsaturated coordinates, extents <= 255)
+    int pad;
+};
+static_assert(sizeof(PackedHdr) == 16, "PackedHdr is one 128-bit load");
+__host__ __device__ inline size_t packed_entries_offset(long long n_tiles) { return ((size_t)n_tiles * 16 + 255) & ~(size_t)255; }
+__device__ __forceinline__ PackedHdr packed_header(const void* packed, unsigned tile) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(packed) + tile);
+    PackedHdr h;
+    h.mnx = (short)(v.x & 0xffff); h.mxx = (short)(v.x >> 16);
+    h.mny = (short)(v.y & 0xffff); h.mxy = (short)(v.y >> 16);
+    h.flags = v.z; h.pad = v.w;
+    return h;
+}
+__device__ __forceinline__ const uint32_t* packed_entries(const void* packed, long long n_tiles) {
+    return reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(packed) + packed_entries_offset(n_tiles));
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -216,6 +239,10 @@ struct Linear {
         int sh;            // 8 * (tap00 byte offset & 3)
         uint32_t W01, W23; // 16-bit lanes {64 w00, 64 w01}, {64 w10, 64 w11}
     };
+    __device__ static __forceinline__ void set_offset(Pixel& p, int off, bool valid) {
+        p.boff = valid ? (off & ~3) : 0;
+        p.sh = (off & 3) * 8;
+    }
     // w00 = 1024 (ax = ay = 0, all other weights 0) is encoded as 65535: (65535 p + 32768) >> 16 is still exactly p.
     __device__ static __forceinline__ void weights(Pixel& p, int ax, int ay, const short*) {
         const int w00 = (32 - ax) * (32 - ay), w01 = ax * (32 - ay), w10 = (32 - ax) * ay, w11 = ax * ay;
@@ -225,13 +252,69 @@ struct Linear {
     // One output pixel from the staged rectangle: the three result bytes [c0 c1 c2 0].
     // `sbuf`: shared-window address of the stage, `pitch`: its row pitch in bytes
     __device__ static __forceinline__ uint32_t sample(uint32_t sbuf, const Pixel& p, uint32_t pitch) {
-        const uint32_t row0 = sbuf + (uint32_t)p.boff;
         uint32_t r0lo, r0hi, r1lo, r1hi;  // byte-aligned: lo = [c0 c1 c2 c0'], hi = [c1' c2' . .]
+        const uint32_t row0 = sbuf + (uint32_t)p.boff;
         lds_taps_aligned(row0, row0 + pitch, p.sh, r0lo, r0hi, r1lo, r1hi);
         const uint32_t q0 = __byte_perm(r0lo, r1lo, 0x7430);  // channel 0: [p00 p01 | p10 p11]
         const uint32_t t0 = __byte_perm(r0lo, r0hi, 0x5241);  // row 0: [c1 c1' | c2 c2']
         const uint32_t t1 = __byte_perm(r1lo, r1hi, 0x5241);  // row 1
         // (sum_t w_t p_t + 512) >> 10 == (sum_t 64 w_t p_t + 32768) >> 16: the result is byte 2 of s (s < 2^24)
+        const uint32_t s0 = __dp2a_hi(p.W23, q0, __dp2a_lo(p.W01, q0, 32768u));
+        const uint32_t s1 = __dp2a_lo(p.W23, t1, __dp2a_lo(p.W01, t0, 32768u));
+        const uint32_t s2 = __dp2a_hi(p.W23, t1, __dp2a_hi(p.W01, t0, 32768u));
+        return __byte_perm(__byte_perm(s0, s1, 0x0062), s2, 0x7610);
+    }
+};
+
+// Bilinear with the byte alignment done by PRMT instead of funnel shifts (EXPERIMENT: VR180_TILED_DEBUG bit 1).
+// The window of a row is bytes s .. s + 5 (s = offset & 3) of the words [a0 a1 (a2)]:
+//   u  = PRMT(a0, a1, selA) = [c0 c0' . .]            c0 at s, c0' at s + 3 <= 6: always inside (a0, a1)
+//   t  = PRMT(a0, a1, selT) = [c1 c1' c2 c2']         offsets s + 1, s + 4, s + 2, s + 5 <= 7 for s <= 2; for s == 3
+//        the third word is loaded into a0's register first (a0 is dead once u exists) and selT = 0x0574 picks
+//        [a1.0 a1.3 a1.1 a0.0]
+// i.e. 5 PRMT per pixel instead of 4 SHF + 3 PRMT.  selA shares a register with the window offset (PRMT reads only
+// the low 16 bits of its selector; the address is one LEA.HI).
+struct LinearP {
+    static constexpr int kPx = 4, kTileH = 32, kLo = 0, kHi = 1, kRowsMin = 32, kInterp = VR180_INTER_LINEAR;
+    static constexpr int kShift = kInterBits;
+    __device__ static __forceinline__ int quant(float m) { return quantise(m); }
+    static constexpr int kStageArea = kStageAreaDefault, kWeightSmem = 0, kOutTiles = 4, kMaxFR = 2;
+    static constexpr bool kRowPatch = true;
+    struct Pixel {
+        uint32_t osel;     // window byte offset (4-aligned) << 16 | selA
+        uint32_t selT;
+        uint32_t W01, W23;
+    };
+    __device__ static __forceinline__ void set_offset(Pixel& p, int off, bool valid) {
+        const uint32_t s = (uint32_t)off & 3u;
+        p.osel = ((valid ? ((uint32_t)off & ~3u) : 0u) << 16) | s | ((s + 3u) << 4);
+        p.selT = s == 3u ? 0x0574u : ((s + 1u) | ((s + 4u) << 4) | ((s + 2u) << 8) | ((s + 5u) << 12));
+    }
+    __device__ static __forceinline__ void weights(Pixel& p, int ax, int ay, const short* t) {
+        Linear::Pixel q;
+        Linear::weights(q, ax, ay, t);
+        p.W01 = q.W01;
+        p.W23 = q.W23;
+    }
+    __device__ static __forceinline__ uint32_t sample(uint32_t sbuf, const Pixel& p, uint32_t pitch) {
+        const uint32_t row0 = sbuf + (p.osel >> 16);
+        uint32_t q0, t0, t1;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b32 a0, a1, b0, b1, u0, u1;\n\t"
+            "setp.eq.u32 p, %6, 0x574;\n\t"
+            "ld.shared.u32 a0, [%3];\n\t"
+            "ld.shared.u32 a1, [%3+4];\n\t"
+            "ld.shared.u32 b0, [%4];\n\t"
+            "ld.shared.u32 b1, [%4+4];\n\t"
+            "prmt.b32 u0, a0, a1, %5;\n\t"
+            "prmt.b32 u1, b0, b1, %5;\n\t"
+            "@p ld.shared.u32 a0, [%3+8];\n\t"
+            "@p ld.shared.u32 b0, [%4+8];\n\t"
+            "prmt.b32 %0, u0, u1, 0x5410;\n\t"
+            "prmt.b32 %1, a0, a1, %6;\n\t"
+            "prmt.b32 %2, b0, b1, %6;\n\t}"
+            : "=&r"(q0), "=&r"(t0), "=&r"(t1)
+            : "r"(row0), "r"(row0 + pitch), "r"(p.osel), "r"(p.selT));
         const uint32_t s0 = __dp2a_hi(p.W23, q0, __dp2a_lo(p.W01, q0, 32768u));
         const uint32_t s1 = __dp2a_lo(p.W23, t1, __dp2a_lo(p.W01, t0, 32768u));
         const uint32_t s2 = __dp2a_hi(p.W23, t1, __dp2a_hi(p.W01, t0, 32768u));
@@ -250,6 +333,10 @@ struct Nearest {
         int boff;  // byte offset (4-aligned) of the 8-byte window that holds the pixel
         int sh;    // 8 * (byte offset & 3)
     };
+    __device__ static __forceinline__ void set_offset(Pixel& p, int off, bool valid) {
+        p.boff = valid ? (off & ~3) : 0;
+        p.sh = (off & 3) * 8;
+    }
     __device__ static __forceinline__ void weights(Pixel&, int, int, const short*) {}
     __device__ static __forceinline__ uint32_t sample(uint32_t sbuf, const Pixel& p, uint32_t) {
         uint32_t a0, a1;
@@ -271,6 +358,10 @@ struct Cubic {
         int sh;
         uint32_t w[8];  // itab[ay][ax][ky][kx] as int16 pairs: w[2 ky] = {kx 0, kx 1}, w[2 ky + 1] = {kx 2, kx 3}
     };
+    __device__ static __forceinline__ void set_offset(Pixel& p, int off, bool valid) {
+        p.boff = valid ? (off & ~3) : 0;
+        p.sh = (off & 3) * 8;
+    }
     __device__ static __forceinline__ void weights(Pixel& p, int ax, int ay, const short* tab) {
         const uint4* t = reinterpret_cast<const uint4*>(tab + ((ay << 5) | ax) * 16);
         const uint4 lo = __ldg(t), hi = __ldg(t + 1);
@@ -322,6 +413,10 @@ struct Lanczos4 {
         const short* w;  // itab[ay][ax][ky][kx], 64 int16 in the table (device memory)
         uint32_t ws;     // shared-window address of the thread's staged copy of them ([tap row][thread] x 16 bytes), 0 = none
     };
+    __device__ static __forceinline__ void set_offset(Pixel& p, int off, bool valid) {
+        p.boff = valid ? (off & ~3) : 0;
+        p.sh = (off & 3) * 8;
+    }
     __device__ static __forceinline__ void weights(Pixel& p, int ax, int ay, const short* tab) {
         p.w = tab + (((ay << 5) | ax) << 6);
         p.ws = 0;
@@ -550,8 +645,7 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
                 for (int k = 0; k < M::kPx; ++k) {
                     const int qx = denorm_q<M>(nx[k], rad, dr.cx), qy = denorm_q<M>(ny[k], rad, dr.cy);
                     const int off = ((qy >> M::kShift) - M::kLo - org.y) * pitch + 3 * ((qx >> M::kShift) - M::kLo) - org.x;
-                    cur[k].boff = cur_have ? (off & ~3) : 0;
-                    cur[k].sh = (off & 3) * 8;
+                    M::set_offset(cur[k], off, cur_have);
                     M::weights(cur[k], qx & 31, qy & 31, tab);
                 }
                 cur_rad = rad;
@@ -735,8 +829,34 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
             }
         }
     } else if (sampler) {
+        // Tile-packed LUT (vr180_pack_lut_tiles): 16-byte tile header + one uint32 per pixel in thread order, i.e. ONE
+        // 128-bit (bilinear / nearest), 64-bit (bicubic) or 32-bit (Lanczos4) coalesced load per thread.
+        bool unpacked = false;
+        if (mv.packed) {
+            const PackedHdr hdr = packed_header(mv.packed, blockIdx.x);
+            if (hdr.flags & 1) {
+                const uint32_t* ent = packed_entries(mv.packed, tp.n_tiles) + ((size_t)blockIdx.x * kSamplers + tid) * kPx;
+                uint32_t e[kPx];
+                if constexpr (kPx == 4) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(ent));
+                    e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w;
+                } else if constexpr (kPx == 2) {
+                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(ent));
+                    e[0] = v.x; e[1] = v.y;
+                } else {
+                    e[0] = __ldg(ent);
+                }
+#pragma unroll
+                for (int k = 0; k < kPx; ++k) {
+                    sx[k] = ((hdr.mnx + (int)(e[k] & 255u)) << M::kShift) | (int)((e[k] >> 16) & 31u);
+                    sy[k] = ((hdr.mny + (int)((e[k] >> 8) & 255u)) << M::kShift) | (int)((e[k] >> 21) & 31u);
+                }
+                unpacked = true;
+            }
+        }
 #pragma unroll
         for (int k = 0; k < kPx; ++k) {
+            if (unpacked) break;
             const int i = x0 + pcol(k), j = y0 + prow(k);
             sx[k] = sy[k] = (int)0x80000000;
             if (i < a.W && j < a.H) {
@@ -981,8 +1101,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     for (int k = 0; k < kPx; ++k) {
         const int ix = sx[k] >> M::kShift, iy = sy[k] >> M::kShift;
         const int off = (iy - M::kLo - ry0) * pitch + 3 * (ix - M::kLo) - bx0;
-        pc[k].boff = off & ~3;
-        pc[k].sh = (off & 3) * 8;
+        M::set_offset(pc[k], off, true);
         if (sampler && !dynr) M::weights(pc[k], sx[k] & 31, sy[k] & 31, tp.tab);
     }
     if constexpr (M::kWeightSmem != 0) {
@@ -1011,7 +1130,97 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     }
 }
 
+// float32 maps -> tile-packed LUT of mode M (one CTA per tile, the thread <-> pixel assignment of k_warp_tiled)
+template <class M>
+__global__ void __launch_bounds__(kSamplers) k_pack_tiles(const float* __restrict__ xmap, const float* __restrict__ ymap,
+                                                         long long map_pitch, int W, int H, int tiles_x, int n_tiles,
+                                                         void* __restrict__ packed) {
+    constexpr int kPx = M::kPx;
+    __shared__ int s_red[kSamplers / 32][4];
+    const int tid = threadIdx.x, lane = tid & 31, sw = tid >> 5;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int x0 = tx * kTileW, y0 = ty * M::kTileH;
+    const bool full_tile = (x0 + kTileW <= W) && (y0 + M::kTileH <= H);
+    int sx[kPx], sy[kPx];
+    int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
+#pragma unroll
+    for (int k = 0; k < kPx; ++k) {
+        const int i = x0 + lane, j = y0 + kPx * sw + k;  // row patches: a warp owns rows kPx sw .. kPx sw + kPx - 1
+        sx[k] = sy[k] = (int)0x80000000;
+        if (i < W && j < H) {
+            sx[k] = M::quant(__ldg(xmap + (long long)j * map_pitch + i));
+            sy[k] = M::quant(__ldg(ymap + (long long)j * map_pitch + i));
+        }
+        const int ix = sat16(sx[k] >> M::kShift), iy = sat16(sy[k] >> M::kShift);
+        mnx = min(mnx, ix); mxx = max(mxx, ix);
+        mny = min(mny, iy); mxy = max(mxy, iy);
+    }
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);
+    mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    if (lane == 0) { s_red[sw][0] = mnx; s_red[sw][1] = mxx; s_red[sw][2] = mny; s_red[sw][3] = mxy; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kSamplers / 32; ++w) {
+        mnx = min(mnx, s_red[w][0]); mxx = max(mxx, s_red[w][1]);
+        mny = min(mny, s_red[w][2]); mxy = max(mxy, s_red[w][3]);
+    }
+    const bool ok = full_tile && mnx > -32768 && mny > -32768 && mxx < 32767 && mxy < 32767 && mxx - mnx <= 255 &&
+                    mxy - mny <= 255;
+    if (tid == 0) {
+        int4 h;
+        h.x = (mnx & 0xffff) | (mxx << 16);
+        h.y = (mny & 0xffff) | (mxy << 16);
+        h.z = ok ? 1 : 0;
+        h.w = 0;
+        reinterpret_cast<int4*>(packed)[blockIdx.x] = h;
+    }
+    uint32_t* ent = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(packed) + packed_entries_offset(n_tiles)) +
+                    ((size_t)blockIdx.x * kSamplers + tid) * kPx;
+#pragma unroll
+    for (int k = 0; k < kPx; ++k) {
+        const int ix = sat16(sx[k] >> M::kShift), iy = sat16(sy[k] >> M::kShift);
+        const uint32_t fx = M::kShift ? (uint32_t)(sx[k] & 31) : 0u, fy = M::kShift ? (uint32_t)(sy[k] & 31) : 0u;
+        ent[k] = ok ? ((uint32_t)(ix - mnx) | ((uint32_t)(iy - mny) << 8) | (fx << 16) | (fy << 21)) : 0u;
+    }
+}
+
 }  // namespace tiled
+
+static int tile_height_of(int interp) {
+    return interp == VR180_INTER_LINEAR || interp == VR180_INTER_NEAREST ? tiled::Linear::kTileH
+           : interp == VR180_INTER_CUBIC                                  ? tiled::Cubic::kTileH
+           : interp == VR180_INTER_LANCZOS4                               ? tiled::Lanczos4::kTileH
+                                                                          : 0;
+}
+
+size_t packed_lut_bytes(int out_w, int out_h, int interp) {
+    const int th = tile_height_of(interp);
+    if (!th) return 0;
+    const long long n_tiles = (long long)((out_w + tiled::kTileW - 1) / tiled::kTileW) * ((out_h + th - 1) / th);
+    return tiled::packed_entries_offset(n_tiles) + (size_t)n_tiles * tiled::kTileW * th * 4;
+}
+
+int launch_pack_lut_tiles(const float* xmap, const float* ymap, int64_t map_pitch, int W, int H, int interp, void* packed,
+                          cudaStream_t st) {
+    using namespace tiled;
+    const int th = tile_height_of(interp);
+    if (!th) return VR180_ERR_UNSUPPORTED;
+    const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + th - 1) / th;
+    const long long n_tiles = (long long)tiles_x * tiles_y;
+    if (n_tiles > 0x7fffffffLL) return VR180_ERR_UNSUPPORTED;
+    const dim3 grid((unsigned)n_tiles);
+    if (interp == VR180_INTER_NEAREST)
+        k_pack_tiles<Nearest><<<grid, kSamplers, 0, st>>>(xmap, ymap, (long long)map_pitch, W, H, tiles_x, (int)n_tiles, packed);
+    else if (interp == VR180_INTER_LINEAR)
+        k_pack_tiles<Linear><<<grid, kSamplers, 0, st>>>(xmap, ymap, (long long)map_pitch, W, H, tiles_x, (int)n_tiles, packed);
+    else if (interp == VR180_INTER_CUBIC)
+        k_pack_tiles<Cubic><<<grid, kSamplers, 0, st>>>(xmap, ymap, (long long)map_pitch, W, H, tiles_x, (int)n_tiles, packed);
+    else
+        k_pack_tiles<Lanczos4><<<grid, kSamplers, 0, st>>>(xmap, ymap, (long long)map_pitch, W, H, tiles_x, (int)n_tiles, packed);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    VR180_CUDA(cudaGetLastError());
+    return VR180_OK;
+}
 
 // Host: recognise the standard chain shape (see StdChain).
 static void match_std_chain(const vr180_chain_t& c, tiled::StdChain& out) {
@@ -1072,16 +1281,24 @@ static bool encode_u8_3d(CUtensorMap* out, const void* base, long long row_bytes
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static int tiled_debug_flags() {  // vr180_debug_set(1, flags), else $VR180_TILED_DEBUG
+    static const int env_debug = [] { const char* e = getenv("VR180_TILED_DEBUG"); return e ? atoi(e) : 0; }();
+    const int set_debug = g_debug_tiled_flags.load(std::memory_order_relaxed);
+    return set_debug >= 0 ? set_debug : env_debug;
+}
+
 constexpr int kMaxFramesPerCta = 64;
 // frames per CTA: the coordinates are evaluated once per CTA, so keep the chunk as large as the grid allows
-static int frames_per_cta(long long tiles, int n_frames) {
+static int frames_per_cta(long long tiles, int n_frames, int views_per_cta = 1) {
     const int forced = g_debug_frames_per_cta.load(std::memory_order_relaxed);  // vr180_debug_set(0, n): tests
     if (forced > 0) return forced < n_frames ? forced : n_frames;
-    // A CTA streams through its frames one after the other, so the CTAs resident at any moment are spread over as many
-    // frames as a chunk holds: beyond kMaxFramesPerCta frames the DRAM / TLB working set of a launch grows faster than
-    // the per-tile prologue amortises (measured: 512 5.7K pairs in ONE chunk 37 us per pair, in chunks of 64 25 us)
+    // A CTA streams through its frames one after the other and the CTAs of neighbouring tiles -- which share the halo
+    // of their source rectangles through L2 -- drift apart the longer they run: beyond ~64 (frame, eye) rectangles per
+    // CTA a launch loses more to that than the per-tile prologue amortises.  Measured, B200: 512 5.7K pairs (both eyes
+    // per CTA) in ONE chunk 37 us per pair, chunks of 128 / 64 / 32 frames 31 / 27 / 25 us; 128 8K pairs (one eye per
+    // CTA) in chunks of 128 / 64 / 32 frames 53.8 / 48.6 / 50.5 us per pair.
     const int cap_set = g_debug_max_frames_per_cta.load(std::memory_order_relaxed);
-    const int cap = cap_set > 0 ? cap_set : kMaxFramesPerCta;
+    const int cap = cap_set > 0 ? cap_set : kMaxFramesPerCta / views_per_cta;
     int fpc = n_frames;
     if (fpc > cap) fpc = (n_frames + (n_frames + cap - 1) / cap - 1) / ((n_frames + cap - 1) / cap);  // equal chunks
     while (fpc > 1 && tiles * ((n_frames + fpc - 1) / fpc) < 148LL * 4 * 2) fpc = (fpc + 1) / 2;
@@ -1173,13 +1390,12 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
     memset(&tp, 0, sizeof(tp));
     const int tiles_x = (a.W + kTileW - 1) / kTileW, tiles_y = (a.H + M::kTileH - 1) / M::kTileH;
     tp.tiles_x = tiles_x;
+    tp.n_tiles = tiles_x * tiles_y;
     tp.tab = tab;
     tp.zero_border = (a.border_mode == VR180_BORDER_CONSTANT && !(a.bv[0] | a.bv[1] | a.bv[2])) ? 1 : 0;
-    static const int env_debug = [] { const char* e = getenv("VR180_TILED_DEBUG"); return e ? atoi(e) : 0; }();
-    const int set_debug = g_debug_tiled_flags.load(std::memory_order_relaxed);
-    tp.debug = set_debug >= 0 ? set_debug : env_debug;
+    tp.debug = tiled_debug_flags();
     const long long tiles = (long long)tiles_x * tiles_y * n_groups;
-    int fpc = frames_per_cta(tiles, a.n_frames);
+    int fpc = frames_per_cta(tiles, a.n_frames, a.share_map ? a.n_views : 1);
     fpc = (fpc + FR - 1) / FR * FR;  // chunks start at multiples of FR: phantom frames can only lie past the batch
     a.frames_per_cta = fpc;
     const int chunks = (a.n_frames + fpc - 1) / fpc;
@@ -1239,13 +1455,19 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
                        : interp == VR180_INTER_CUBIC ? tiled::Cubic::kTileH
                                                      : tiled::Lanczos4::kTileH;
     const long long tiles = (long long)((a0.W + tiled::kTileW - 1) / tiled::kTileW) * ((a0.H + tile_h - 1) / tile_h) * n_groups;
-    const bool pairs = !dyn && frames_per_cta(tiles, a0.n_frames) >= 2;
+    const int vpc = a0.share_map ? a0.n_views : 1;
+    const bool pairs = !dyn && frames_per_cta(tiles, a0.n_frames, vpc) >= 2;
     if (interp == VR180_INTER_NEAREST) {
         if (dyn) return launch_mode<tiled::Nearest, true, 1>(a0, c0, c1, nullptr, st);
         return pairs ? launch_mode<tiled::Nearest, false, 2>(a0, c0, c1, nullptr, st)
                      : launch_mode<tiled::Nearest, false, 1>(a0, c0, c1, nullptr, st);
     }
     if (interp == VR180_INTER_LINEAR) {
+        if (tiled_debug_flags() & 2) {  // experiment: PRMT byte alignment
+            if (dyn) return launch_mode<tiled::LinearP, true, 1>(a0, c0, c1, nullptr, st);
+            return pairs ? launch_mode<tiled::LinearP, false, 2>(a0, c0, c1, nullptr, st)
+                         : launch_mode<tiled::LinearP, false, 1>(a0, c0, c1, nullptr, st);
+        }
         if (dyn) return launch_mode<tiled::Linear, true, 1>(a0, c0, c1, nullptr, st);
         return pairs ? launch_mode<tiled::Linear, false, 2>(a0, c0, c1, nullptr, st)
                      : launch_mode<tiled::Linear, false, 1>(a0, c0, c1, nullptr, st);
@@ -1257,7 +1479,7 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
                      : launch_mode<tiled::Lanczos4, false, 1>(a0, c0, c1, weight_tab, st);
     }
     if (dyn) return launch_mode<tiled::Cubic, true, 1>(a0, c0, c1, weight_tab, st);
-    if (frames_per_cta(tiles, a0.n_frames) >= 8) return launch_mode<tiled::Cubic, false, 4>(a0, c0, c1, weight_tab, st);
+    if (frames_per_cta(tiles, a0.n_frames, vpc) >= 8) return launch_mode<tiled::Cubic, false, 4>(a0, c0, c1, weight_tab, st);
     return pairs ? launch_mode<tiled::Cubic, false, 2>(a0, c0, c1, weight_tab, st)
                  : launch_mode<tiled::Cubic, false, 1>(a0, c0, c1, weight_tab, st);
 }

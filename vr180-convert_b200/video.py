@@ -7,6 +7,7 @@ HBM (torch CUDA tensors are only the buffer type) is warped by one kernel launch
   * map_source="analytic": the fused kernel evaluates the chain per output pixel in registers -- no LUT exists;
   * map_source="lut":      float32 maps built once (k_build_map, or the host for opaque transformers), cached;
   * map_source="lut_fixed": the maps quantised once to cv2's fixed-point (k_pack_lut), cached;
+  * map_source="lut_packed": the tile-packed 4-byte LUT (k_pack_tiles): one 128-bit load per thread, cached;
   * radius="auto": k_get_radius per frame (max over the two eyes) feeds the warp kernel through device memory.
 
 Frames of a clip are independent, so multi-GPU runs shard them statically with `shard_range` (no collective).
@@ -38,7 +39,7 @@ class SbsWarper:
         boarder_mode: int = BORDER_CONSTANT,
         boarder_value: Any = 0,
         radius: float | Sequence[float] | Literal["auto", "max"] = "max",
-        map_source: Literal["analytic", "lut", "lut_fixed"] = "analytic",
+        map_source: Literal["analytic", "lut", "lut_fixed", "lut_packed"] = "analytic",
         channels: int = 3,
         threshold: float = 10,
         device: Any = None,
@@ -77,6 +78,7 @@ class SbsWarper:
         self._chains = [N.make_chain(o) if o is not None else None for o in self._lowered]
         self._maps = None   # (n_maps, 2, H, W) float32 on device
         self._fixed = None  # (n_maps, H, W, 2) int32 on device
+        self._packed = None  # n_maps tile-packed LUTs (uint8 buffers) on device, built for self.interpolation
         self._radius_buf = None
         self._trans_buf = None
 
@@ -111,6 +113,24 @@ class SbsWarper:
                                                fixed[m].data_ptr(), self.w, stream), "vr180_pack_lut")
             self._fixed = fixed
         return self._fixed
+
+    def packed_lut(self):
+        """Tile-packed LUT (vr180_pack_lut_tiles) per map for this plan's interpolation: 16-byte tile headers + 4 bytes
+        per pixel in the tiled kernel's thread order; the float32 maps stay alongside for tiles that cannot be packed."""
+        torch = self.torch
+        if self._packed is None:
+            maps = self.maps()
+            lib = N.lib()
+            nbytes = int(lib.vr180_packed_lut_bytes(self.w, self.h, self.interpolation))
+            if nbytes == 0:
+                raise ValueError("no tiled mode for this interpolation")
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            packed = torch.empty((maps.shape[0], nbytes), dtype=torch.uint8, device=self.device)
+            for m in range(maps.shape[0]):
+                N.check(lib.vr180_pack_lut_tiles(maps[m, 0].data_ptr(), maps[m, 1].data_ptr(), self.w, self.w, self.h,
+                                                 self.interpolation, packed[m].data_ptr(), stream), "vr180_pack_lut_tiles")
+            self._packed = packed
+        return self._packed
 
     # --- per batch ---------------------------------------------------------------------------------------
     def _image(self, t) -> N.Image:
@@ -173,6 +193,11 @@ class SbsWarper:
                 maps = self.maps()
                 vw.map.kind = N.MAPSRC_FLOAT2
                 vw.map.xmap, vw.map.ymap, vw.map.map_pitch = maps[m, 0].data_ptr(), maps[m, 1].data_ptr(), self.w
+            elif self.map_source == "lut_packed":
+                maps, packed = self.maps(), self.packed_lut()
+                vw.map.kind = N.MAPSRC_PACKED
+                vw.map.xmap, vw.map.ymap, vw.map.map_pitch = maps[m, 0].data_ptr(), maps[m, 1].data_ptr(), self.w
+                vw.map.packed, vw.map.packed_interpolation = packed[m].data_ptr(), self.interpolation
             else:
                 fixed = self.fixed_lut()
                 vw.map.kind = N.MAPSRC_FIXED
