@@ -234,6 +234,25 @@ int vr180_get_radius(const vr180_image_t* views, int n_views, int n_frames, doub
                      int32_t* transitions_dev, double* radius_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * (4) anaglyph merge -- replaces the merge=True branch of apply_lr (remapper.py:485-498) on the device-resident SBS
+ *     frame (H, 2 * eye_w, 3): out[y, x, c] = (mean_c L[y, x] * (0, 128, 255)[c] + mean_c R[y, x] * (255, 128, 0)[c]) / 255
+ *     in float64 with one rounding per NumPy ufunc, then the float64 -> uint8 conversion cv.imwrite applies to the
+ *     reference's float64 image (round half to even, saturate).  The "L" / "R" labels (cv.putText, :499-516) stay on
+ *     the host: on a float64 image OpenCV draws them without anti-aliasing, i.e. as pure colours over these bytes.
+ * ---------------------------------------------------------------------------------------------------- */
+int vr180_anaglyph(const uint8_t* sbs_dev, int64_t sbs_pitch, int64_t sbs_frame_stride, int eye_w, int h, int n_frames,
+                   uint8_t* out_dev, int64_t out_pitch, int64_t out_frame_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * (5) chain on points -- the pixel -> 3-D step of match_lr (remapper.py:291-320: (decoder * Denormalize)
+ *     .inverse_transform on the matched points, then equidistant_to_3d, transformer.py:483-508) for a batch of points.
+ *     `chain` is applied to (x[i], y[i]) in float64; out_x / out_y receive the transformed coordinates and/or out_v3
+ *     the n x 3 unit vectors of equidistant_to_3d of the result (either may be NULL, not both).
+ * ---------------------------------------------------------------------------------------------------- */
+int vr180_transform_points(const vr180_chain_t* chain, int64_t n, const double* x_dev, const double* y_dev,
+                           double* out_x_dev, double* out_y_dev, double* out_v3_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * Host-buffer pipeline (what the Python `apply` / `apply_lr` call with NumPy arrays): a context owns device
  * staging buffers and three streams (H2D, compute, D2H) and runs upload -> [get_radius] -> warp -> download
  * for a batch of frames with the copies of neighbouring frames overlapped.
@@ -293,6 +312,10 @@ typedef struct vr180_host_job {
        staging: VR180_STAGE_AUTO = per buffer, decided with cudaPointerGetAttributes; ALWAYS / NEVER force it. */
     int32_t staging;
     int32_t copy_threads;
+    /* merge != 0 (n_views == 2, 3 channels): vr180_anaglyph runs on the device SBS frame and the destination frames
+       are the merged (out_h, out_w, 3) images -- half the download, no host pass (apply_lr(merge=True)). */
+    int32_t merge;
+    int32_t reserved2;
 } vr180_host_job_t;
 
 enum { VR180_STAGE_AUTO = 0, VR180_STAGE_ALWAYS = 1, VR180_STAGE_NEVER = 2 };

@@ -214,3 +214,14 @@ def apply_lr_sbs(src_l, src_r, maps_l, maps_r, interpolation=INTER_LINEAR, borde
     left = remap(src_l, maps_l[0], maps_l[1], interpolation, border_mode, border_value)
     right = remap(src_r, maps_r[0], maps_r[1], interpolation, border_mode, border_value)
     return np.concatenate([left, right], axis=1)
+
+
+def anaglyph_u8(left: np.ndarray, right: np.ndarray) -> np.ndarray:
+    """apply_lr(merge=True) without the text labels (/root/reference/src/vr180_convert/remapper.py:485-498), followed
+    by the float64 -> uint8 conversion cv.imwrite applies to the reference's float64 image (round half to even,
+    saturate; verified against cv2.imwrite + imread)."""
+    colors = [(0, 128, 255), (255, 128, 0)]
+    combine = np.mean(left, axis=-1)[..., None] * np.array(colors[0]).reshape([1] * (left.ndim - 1) + [3]) + (
+        np.mean(right, axis=-1)[..., None] * np.array(colors[1]).reshape([1] * (right.ndim - 1) + [3]))
+    combine /= 255
+    return np.clip(np.rint(combine), 0, 255).astype(np.uint8)

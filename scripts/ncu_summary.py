@@ -43,7 +43,11 @@ def main():
     for h in hdr:
         if "issue_stalled" in h and "per_issue_active" in h and "not_issued" not in h:
             lines.append(f"{h} [{d[h][0]}] {d[h][1]}")
-    (ROOT / "profiles" / f"r1_{tag}_ncu_summary.txt").write_text("\n".join(lines) + "\n")
+    out_dir = ROOT / (sys.argv[5] if len(sys.argv) > 5 else "profiles")
+    (out_dir / f"{tag}_ncu_summary.txt").write_text("\n".join(lines) + "\n")
+    if out_dir.name != "profiles":
+        print("\n".join(lines[:14]))
+        return
 
     def gb(name):
         u, v = d[name]
@@ -54,7 +58,7 @@ def main():
     traffic = json.loads(tp.read_text()) if tp.exists() else {}
     traffic[workload] = {"pairs_per_launch": pairs, "dram_bytes_per_launch": gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum"),
                          "dram_bytes_read": gb("dram__bytes_read.sum"), "dram_bytes_write": gb("dram__bytes_write.sum"),
-                         "source": f"profiles/r1_{tag}_ncu_summary.txt (ncu --set full, one launch)"}
+                         "source": f"profiles/{tag}_ncu_summary.txt (ncu --set full, one launch)"}
     tp.write_text(json.dumps(traffic, indent=1) + "\n")
     print("\n".join(lines[:12]))
 

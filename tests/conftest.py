@@ -52,6 +52,12 @@ def golden_cfg1():
     return z, json.loads(str(z["meta"])), GOLDEN / "cfg1_test.jpg"
 
 
+@pytest.fixture(scope="session")
+def golden_merge_match():
+    """apply_lr(merge=True) outputs and match_lr vectors of the unmodified reference (make_golden.py merge)."""
+    return np.load(GOLDEN / "merge_match.npz")
+
+
 def disc_frame(h: int, w: int, seed: int, margin: int = 8) -> np.ndarray:
     """Synthetic fisheye frame of SURVEY.md §8(d): uniform random bytes inside the disc, zeros outside."""
     rng = np.random.default_rng(seed)

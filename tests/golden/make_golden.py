@@ -197,6 +197,43 @@ def make_apply():
     print("apply.npz")
 
 
+def make_merge_and_match():
+    """apply_lr(merge=True) (remapper.py:485-516: float64 anaglyph + putText labels + imwrite's uint8 conversion) and
+    match_lr (remapper.py:251-321) through the unmodified reference."""
+    card = generate_test_image(256)
+    left, right = card[:, :128], card[:, 128:]
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        for name, size in (("small", (96, 80)), ("labels", (512, 1024))):  # 1024 rows: font scale 1, labels drawn
+            p = Path(d) / "m.png"
+            ref.apply_lr(eval(CASES["rot_poly"][0], NS), left_path=left, right_path=right, out_path=p,  # noqa: S307
+                         size_output=size, interpolation=cv2.INTER_LINEAR, radius="max", merge=True)
+            out[f"merge/{name}"] = cv2.imread(str(p))
+        tl = eval(CASES["rot_poly"][0], NS)  # noqa: S307
+        tr = eval(CASES["rot_nonunit"][0], NS)  # noqa: S307
+        p = Path(d) / "m2.png"
+        ref.apply_lr((tl, tr), left_path=left, right_path=right, out_path=p, size_output=(96, 80),
+                     interpolation=cv2.INTER_CUBIC, radius="auto", merge=True)
+        out["merge/tuple_auto"] = cv2.imread(str(p))
+        # match_lr reads files
+        pl, pr = Path(d) / "l.png", Path(d) / "r.png"
+        cv2.imwrite(str(pl), np.ascontiguousarray(left))
+        cv2.imwrite(str(pr), np.ascontiguousarray(right))
+        rng = np.random.default_rng(5)
+        pts_l = rng.uniform(20, 108, (24, 2))
+        pts_r = pts_l + rng.normal(0, 1.5, (24, 2))
+        out["match/pts_l"], out["match/pts_r"] = pts_l, pts_r
+        dec = ref_t.FisheyeDecoder("equidistant")
+        for rname, radius in (("max", "max"), ("auto", "auto"), ("60.5", 60.5)):
+            vl, vr = ref_remapper.match_lr(dec, pts_l, pts_r, [pl, pr], radius=radius)
+            out[f"match/single/{rname}/vl"], out[f"match/single/{rname}/vr"] = vl, vr
+        dec2 = (ref_t.FisheyeDecoder("stereographic"), ref_t.ZoomTransformer(1.1) * ref_t.FisheyeDecoder("equisolid"))
+        vl, vr = ref_remapper.match_lr(dec2, pts_l, pts_r, [pl, pr], radius=70.0)
+        out["match/tuple/70.0/vl"], out["match/tuple/70.0/vr"] = vl, vr
+    np.savez_compressed(HERE / "merge_match.npz", **out)
+    print("merge_match.npz", {k: v.shape for k, v in out.items()})
+
+
 def make_cfg1():
     """BASELINE.json configs[0]: `v1c lr test.jpg test.jpg --transformer 'EquirectangularEncoder()
     * PolynomialScaler() * FisheyeDecoder("equidistant")' --interpolation INTER_LINEAR` with the CLI's default size
@@ -238,9 +275,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cfg1":
         make_cfg1()
         raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "merge":
+        make_merge_and_match()
+        raise SystemExit(0)
     make_maps()
     make_big_map_hashes()
     make_remap()
     make_radius()
     make_apply()
+    make_merge_and_match()
     make_cfg1()

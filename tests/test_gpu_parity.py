@@ -561,3 +561,48 @@ def test_packed_lut_tiles_with_unpackable_tiles(interp):
     for f in range(2):
         want = np.concatenate([cv2.remap(src[f], xm, ym, interpolation=interp), cv2.remap(src[1 - f], xm, ym, interpolation=interp)], axis=1)
         assert np.array_equal(got[f], want), (interp, f, int((got[f] != want).sum()))
+
+
+def test_apply_lr_merge_matches_reference_golden(golden_merge_match, golden_apply, golden_maps, tmp_path):
+    """apply_lr(merge=True) (remapper.py:485-516): device anaglyph kernel + host labels == the reference's PNG, with
+    and without labels (font scale rows // 1000), shared transformer and per-eye tuple with radius="auto"."""
+    g = golden_merge_match
+    _, meta = golden_maps
+    card = golden_apply["card"]
+    left, right = card[:, :128], card[:, 128:]
+    t = eval(meta["cases"]["rot_poly"]["expr"], NS)  # noqa: S307
+    out = tmp_path / "m.png"
+    for name, size in (("small", (96, 80)), ("labels", (512, 1024))):
+        V.apply_lr(t, left_path=left, right_path=right, out_path=out, size_output=size, interpolation=1, radius="max",
+                   merge=True)
+        got = cv2.imread(str(out))
+        assert got.shape == g[f"merge/{name}"].shape and np.array_equal(got, g[f"merge/{name}"]), name
+    tr = eval(meta["cases"]["rot_nonunit"]["expr"], NS)  # noqa: S307
+    V.apply_lr((t, tr), left_path=left, right_path=right, out_path=out, size_output=(96, 80), interpolation=2,
+               radius="auto", merge=True)
+    assert np.array_equal(cv2.imread(str(out)), g["merge/tuple_auto"])
+    # the device kernel alone against the oracle restatement on random eyes (incl. exact .5 ties of the float64 value)
+    rng = np.random.default_rng(3)
+    a, b = rng.integers(0, 256, (2, 70, 90, 3), dtype=np.uint8)
+    from vr180_convert_b200.remapper import _merge_device
+
+    assert np.array_equal(_merge_device(a, b), remap_np.anaglyph_u8(a, b))
+
+
+def test_match_lr_matches_reference_golden(golden_merge_match, golden_apply):
+    """match_lr (remapper.py:251-321): vr180_transform_points (float64) vs the reference's float32 NumPy chain."""
+    g = golden_merge_match
+    card = golden_apply["card"]
+    imgs = [np.ascontiguousarray(card[:, :128]), np.ascontiguousarray(card[:, 128:])]
+    pts_l, pts_r = g["match/pts_l"], g["match/pts_r"]
+    dec = V.FisheyeDecoder("equidistant")
+    for rname, radius in (("max", "max"), ("auto", "auto"), ("60.5", 60.5)):
+        vl, vr = V.match_lr(dec, pts_l, pts_r, imgs, radius=radius)
+        np.testing.assert_allclose(vl, g[f"match/single/{rname}/vl"], rtol=0, atol=3e-6, equal_nan=True)
+        np.testing.assert_allclose(vr, g[f"match/single/{rname}/vr"], rtol=0, atol=3e-6, equal_nan=True)
+    dec2 = (V.FisheyeDecoder("stereographic"), V.ZoomTransformer(1.1) * V.FisheyeDecoder("equisolid"))
+    vl, vr = V.match_lr(dec2, pts_l, pts_r, imgs, radius=70.0)
+    np.testing.assert_allclose(vl, g["match/tuple/70.0/vl"], rtol=0, atol=3e-6, equal_nan=True)
+    np.testing.assert_allclose(vr, g["match/tuple/70.0/vr"], rtol=0, atol=3e-6, equal_nan=True)
+    with pytest.raises(ValueError):
+        V.match_lr(dec, pts_l[:3], pts_r, imgs, radius=50.0)

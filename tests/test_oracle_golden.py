@@ -149,3 +149,23 @@ def test_cfg1_reference_cli_run(golden_cfg1):
     assert bad <= 4, bad  # another libm may flip a vanishing number of float32 map values by one ulp
     if bad == 0 and np.__version__ == meta["numpy"]:
         assert hashlib.sha256(out.tobytes()).hexdigest() == meta["output_sha256"]
+
+
+def test_anaglyph_oracle_matches_reference_merge(golden_merge_match, golden_apply):
+    """remap_np.anaglyph_u8 (+ LINE_8 labels) == the PNG the reference's apply_lr(merge=True) writes."""
+    g = golden_merge_match
+    card = golden_apply["card"]
+    left, right = card[:, :128], card[:, 128:]
+    ops = [("equirect_enc", True), ("rot3", chain_np.quat_to_matrix(0.9999093510664558, 0.00500054686470522, 0.01000109372941044,
+                                                                      -0.00750082029705783).ravel().tolist()),
+           ("poly", [0, 1, -0.02, 0.003]), ("fisheye_dec", "equidistant")]
+    for name, size in (("small", (96, 80)), ("labels", (512, 1024))):
+        xm, ym = chain_np.get_map(ops, radius=64.0, size_input=(256, 128), size_output=size)  # radius "max" = min(h/2, w/2)
+        eyes = [cv2.remap(np.ascontiguousarray(e), xm, ym, interpolation=cv2.INTER_LINEAR) for e in (left, right)]
+        got = remap_np.anaglyph_u8(eyes[0], eyes[1])
+        colors = [(0, 128, 255), (255, 128, 0)]
+        got = np.ascontiguousarray(got)
+        cv2.putText(got, "L", (0, len(got[1]) // 10), cv2.FONT_HERSHEY_SIMPLEX, len(got) // 1000, colors[0], 2, cv2.LINE_8)
+        cv2.putText(got, "R", (len(got[1]) // 2, len(got[0]) // 10), cv2.FONT_HERSHEY_SIMPLEX, len(got) // 1000, colors[1],
+                    2, cv2.LINE_8)
+        assert np.array_equal(got, g[f"merge/{name}"]), name

@@ -67,7 +67,7 @@ class HostJob(C.Structure):
                 ("dst", C.c_void_p), ("dst_pitch", C.c_int64), ("dst_frame_stride", C.c_int64),
                 ("transitions_out", C.c_void_p), ("radius_out", C.c_void_p),
                 ("src_frames", C.POINTER(C.c_void_p) * 2), ("dst_frames", C.POINTER(C.c_void_p)),
-                ("staging", C.c_int32), ("copy_threads", C.c_int32)]
+                ("staging", C.c_int32), ("copy_threads", C.c_int32), ("merge", C.c_int32), ("reserved2", C.c_int32)]
 
 
 # every symbol include/vr180_b200.h declares: name -> (restype, argtypes)
@@ -85,6 +85,10 @@ SYMBOLS = {
     "vr180_pack_lut_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                        C.c_void_p]),
     "vr180_remap": (C.c_int, [C.POINTER(RemapParams), C.c_void_p]),
+    "vr180_anaglyph": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                 C.c_int64, C.c_void_p]),
+    "vr180_transform_points": (C.c_int, [C.POINTER(Chain), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
     "vr180_get_radius": (C.c_int, [C.POINTER(Image), C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
     "vr180_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),

@@ -125,6 +125,27 @@ int vr180_remap(const vr180_remap_params_t* params, void* stream) {
     return launch_remap(params, (cudaStream_t)stream);
 }
 
+int vr180_anaglyph(const uint8_t* sbs_dev, int64_t sbs_pitch, int64_t sbs_frame_stride, int eye_w, int h, int n_frames,
+                   uint8_t* out_dev, int64_t out_pitch, int64_t out_frame_stride, void* stream) {
+    if (!sbs_dev || !out_dev || eye_w <= 0 || h <= 0 || n_frames < 0 || sbs_pitch < (int64_t)eye_w * 6 ||
+        out_pitch < (int64_t)eye_w * 3)
+        return VR180_ERR_INVALID_ARG;
+    DeviceGuard g(out_dev);
+    if (!g.ok) return VR180_ERR_INVALID_ARG;
+    return launch_anaglyph(sbs_dev, sbs_pitch, sbs_frame_stride, eye_w, h, n_frames, out_dev, out_pitch, out_frame_stride,
+                           (cudaStream_t)stream);
+}
+
+int vr180_transform_points(const vr180_chain_t* chain, int64_t n, const double* x_dev, const double* y_dev,
+                           double* out_x_dev, double* out_y_dev, double* out_v3_dev, void* stream) {
+    if (!chain || n < 0 || !x_dev || !y_dev || (!out_v3_dev && !(out_x_dev && out_y_dev))) return VR180_ERR_INVALID_ARG;
+    const int rc = validate_chain(chain);
+    if (rc != VR180_OK) return rc;
+    DeviceGuard g(x_dev);
+    if (!g.ok) return VR180_ERR_INVALID_ARG;
+    return launch_transform_points(chain, n, x_dev, y_dev, out_x_dev, out_y_dev, out_v3_dev, (cudaStream_t)stream);
+}
+
 int vr180_get_radius(const vr180_image_t* views, int n_views, int n_frames, double threshold, int32_t* transitions_dev,
                      double* radius_dev, void* stream) {
     if (!views || (!transitions_dev && !radius_dev)) return VR180_ERR_INVALID_ARG;

@@ -395,4 +395,77 @@ int launch_get_radius(const vr180_image_t* views, int n_views, int n_frames, dou
     return VR180_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// k_anaglyph: the merge=True branch of apply_lr (remapper.py:485-498) on the device-resident SBS frame
+// ---------------------------------------------------------------------------------------------------------
+// combine = mean_c(L)[..., None] * (0, 128, 255) + mean_c(R)[..., None] * (255, 128, 0);  combine /= 255   (float64,
+// one rounding per NumPy ufunc), then cv.imwrite's float64 -> uint8 conversion (round half to even, saturate).
+__global__ void __launch_bounds__(256) k_anaglyph(const uint8_t* __restrict__ sbs, long long pitch, long long frame_stride,
+                                                  int W, int H, uint8_t* __restrict__ out, long long out_pitch,
+                                                  long long out_frame_stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= W) return;
+    const uint8_t* row = sbs + (long long)blockIdx.z * frame_stride + (long long)j * pitch;
+    const uint8_t* l = row + (long long)i * 3;
+    const uint8_t* r = row + (long long)(W + i) * 3;
+    const double ml = __ddiv_rn((double)(__ldg(l) + __ldg(l + 1) + __ldg(l + 2)), 3.0);  // np.mean(axis=-1)
+    const double mr = __ddiv_rn((double)(__ldg(r) + __ldg(r + 1) + __ldg(r + 2)), 3.0);
+    const double cl[3] = {0.0, 128.0, 255.0}, cr[3] = {255.0, 128.0, 0.0};
+    uint8_t* o = out + (long long)blockIdx.z * out_frame_stride + (long long)j * out_pitch + (long long)i * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double v = __ddiv_rn(__dadd_rn(__dmul_rn(ml, cl[c]), __dmul_rn(mr, cr[c])), 255.0);
+        o[c] = (uint8_t)min(255, max(0, __double2int_rn(v)));
+    }
+}
+
+int launch_anaglyph(const uint8_t* sbs, int64_t pitch, int64_t frame_stride, int W, int H, int n_frames, uint8_t* out,
+                    int64_t out_pitch, int64_t out_frame_stride, cudaStream_t st) {
+    if (n_frames == 0) return VR180_OK;
+    if (H > 65535 || n_frames > 65535) return VR180_ERR_UNSUPPORTED;
+    dim3 grid((W + 255) / 256, H, n_frames);
+    k_anaglyph<<<grid, 256, 0, st>>>(sbs, pitch, frame_stride, W, H, out, out_pitch, out_frame_stride);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    VR180_CUDA(cudaGetLastError());
+    return VR180_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_transform_points: a lowered chain on arbitrary points (match_lr's pixel -> 3-D step, remapper.py:291-320)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_transform_points(const __grid_constant__ vr180_chain_t chain, long long n,
+                                                          const double* __restrict__ x, const double* __restrict__ y,
+                                                          double* __restrict__ ox, double* __restrict__ oy,
+                                                          double* __restrict__ v3) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ChainState s;
+    s.mode = MODE_XY;
+    s.x = __ldg(x + i);
+    s.y = __ldg(y + i);
+    s.r = s.ux = s.uy = s.vx = s.vy = s.vz = 0.0;
+    run_ops(chain, 0, chain.n_ops, s);
+    if (v3) {  // equidistant_to_3d (transformer.py:483-508)
+        to_vec3(s);
+        v3[3 * i + 0] = s.vx;
+        v3[3 * i + 1] = s.vy;
+        v3[3 * i + 2] = s.vz;
+    }
+    if (ox && oy) {
+        to_xy(s);
+        ox[i] = s.x;
+        oy[i] = s.y;
+    }
+}
+
+int launch_transform_points(const vr180_chain_t* chain, long long n, const double* x, const double* y, double* ox,
+                            double* oy, double* v3, cudaStream_t st) {
+    if (n == 0) return VR180_OK;
+    k_transform_points<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(*chain, n, x, y, ox, oy, v3);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    VR180_CUDA(cudaGetLastError());
+    return VR180_OK;
+}
+
 }  // namespace vr180

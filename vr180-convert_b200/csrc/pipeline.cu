@@ -204,7 +204,7 @@ void run_copies(CopyPool& pool, const std::vector<Copy2D>& copies) {
 }
 
 struct Slot {
-    DevBuf src[2], dst;
+    DevBuf src[2], dst, merged;
     PinBuf h_src[2], h_dst;
     cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
 };
@@ -291,6 +291,7 @@ static void ctx_free(vr180_ctx* c) {
             s.h_src[v].release();
         }
         s.dst.release();
+        s.merged.release();
         s.h_dst.release();
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_comp) cudaEventDestroy(s.ev_comp);
@@ -361,6 +362,10 @@ static int ctx_run_locked(vr180_ctx* c, const vr180_host_job_t* job) {
     const size_t src_frame = src_pitch * job->src_rows;
     const size_t dst_row = (size_t)job->out_w * V * C, dst_pitch = align_up(dst_row, 16);
     const size_t dst_frame = dst_pitch * job->out_h;
+    // what goes back to the host: the SBS frame, or (merge) the anaglyph of its two halves
+    const bool merge = job->merge != 0;
+    const size_t out_row = merge ? (size_t)job->out_w * C : dst_row, out_pitch = align_up(out_row, 16);
+    const size_t out_frame = out_pitch * job->out_h;
 
     auto src_of = [&](int v, int f) -> const uint8_t* {
         return scattered ? job->src_frames[v][f] : job->src[v] + (size_t)f * job->src_frame_stride[v];
@@ -378,7 +383,7 @@ static int ctx_run_locked(vr180_ctx* c, const vr180_host_job_t* job) {
     }
 
     // frames per chunk: ~kChunkBytes of traffic per chunk, at least two chunks so that copies overlap compute
-    const size_t per_frame = src_frame * V + dst_frame;
+    const size_t per_frame = src_frame * V + dst_frame + (merge ? out_frame : 0);
     int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)F, kChunkBytes / std::max<size_t>(per_frame, 1)));
     if (F >= 2) chunk = std::min(chunk, (F + 1) / 2);
     const int n_chunks = (F + chunk - 1) / chunk;
@@ -391,7 +396,8 @@ static int ctx_run_locked(vr180_ctx* c, const vr180_host_job_t* job) {
             if (stage_in && (rc = sl.h_src[v].reserve(src_frame * chunk)) != VR180_OK) return rc;
         }
         if ((rc = sl.dst.reserve(dst_frame * chunk)) != VR180_OK) return rc;
-        if (stage_out && (rc = sl.h_dst.reserve(dst_frame * chunk)) != VR180_OK) return rc;
+        if (merge && (rc = sl.merged.reserve(out_frame * chunk)) != VR180_OK) return rc;
+        if (stage_out && (rc = sl.h_dst.reserve(out_frame * chunk)) != VR180_OK) return rc;
     }
     if ((rc = c->trans.reserve(sizeof(int32_t) * 2 * V * F)) != VR180_OK) return rc;
     if ((rc = c->radius.reserve(sizeof(double) * F)) != VR180_OK) return rc;
@@ -512,17 +518,23 @@ static int ctx_run_locked(vr180_ctx* c, const vr180_host_job_t* job) {
         }
         rc = launch_remap(&p, c->s_comp);
         if (rc != VR180_OK) return rc;
+        if (merge) {
+            rc = launch_anaglyph((const uint8_t*)sl.dst.p, (int64_t)dst_pitch, (int64_t)dst_frame, job->out_w, job->out_h, nf,
+                                 (uint8_t*)sl.merged.p, (int64_t)out_pitch, (int64_t)out_frame, c->s_comp);
+            if (rc != VR180_OK) return rc;
+        }
+        const uint8_t* d_out = (const uint8_t*)(merge ? sl.merged.p : sl.dst.p);
         VR180_CUDA(cudaEventRecord(sl.ev_comp, c->s_comp));
         // --- download -----------------------------------------------------------------------------------
         VR180_CUDA(cudaStreamWaitEvent(c->s_d2h, sl.ev_comp, 0));
         if (stage_out) {
             if (slot_ticket[s]) c->wait_drained(slot_ticket[s]);  // the slot's pinned dst has been unpacked
-            VR180_CUDA(cudaMemcpyAsync(sl.h_dst.p, sl.dst.p, dst_frame * nf, cudaMemcpyDeviceToHost, c->s_d2h));
+            VR180_CUDA(cudaMemcpyAsync(sl.h_dst.p, d_out, out_frame * nf, cudaMemcpyDeviceToHost, c->s_d2h));
             VR180_CUDA(cudaEventRecord(sl.ev_d2h, c->s_d2h));
             std::vector<Copy2D> cp;
             for (int f = 0; f < nf; ++f)
-                cp.push_back({dst_of(f0 + f), (const uint8_t*)sl.h_dst.p + (size_t)f * dst_frame, (size_t)job->dst_pitch,
-                              dst_pitch, dst_row, (size_t)job->out_h});
+                cp.push_back({dst_of(f0 + f), (const uint8_t*)sl.h_dst.p + (size_t)f * out_frame, (size_t)job->dst_pitch,
+                              out_pitch, out_row, (size_t)job->out_h});
             cudaEvent_t ev = sl.ev_d2h;
             slot_ticket[s] = c->push_drain([pool, ev, cp] {
                 cudaEventSynchronize(ev);
@@ -532,19 +544,19 @@ static int ctx_run_locked(vr180_ctx* c, const vr180_host_job_t* job) {
         }
         const size_t hd_pitch = (size_t)job->dst_pitch;
         const bool dense_out = !job->dst_frames && (size_t)job->dst_frame_stride == hd_pitch * job->out_h;
-        if (dense_out && hd_pitch == dst_pitch) {
-            VR180_CUDA(cudaMemcpyAsync(dst_of(f0), sl.dst.p, dst_frame * nf, cudaMemcpyDeviceToHost, c->s_d2h));
+        if (dense_out && hd_pitch == out_pitch) {
+            VR180_CUDA(cudaMemcpyAsync(dst_of(f0), d_out, out_frame * nf, cudaMemcpyDeviceToHost, c->s_d2h));
         } else if (dense_out) {
-            VR180_CUDA(cudaMemcpy2DAsync(dst_of(f0), hd_pitch, sl.dst.p, dst_pitch, dst_row, (size_t)job->out_h * nf,
+            VR180_CUDA(cudaMemcpy2DAsync(dst_of(f0), hd_pitch, d_out, out_pitch, out_row, (size_t)job->out_h * nf,
                                          cudaMemcpyDeviceToHost, c->s_d2h));
         } else {
             for (int f = 0; f < nf; ++f) {
-                if (hd_pitch == dst_pitch)
-                    VR180_CUDA(cudaMemcpyAsync(dst_of(f0 + f), (uint8_t*)sl.dst.p + f * dst_frame, dst_frame,
+                if (hd_pitch == out_pitch)
+                    VR180_CUDA(cudaMemcpyAsync(dst_of(f0 + f), d_out + f * out_frame, out_frame,
                                                cudaMemcpyDeviceToHost, c->s_d2h));
                 else
-                    VR180_CUDA(cudaMemcpy2DAsync(dst_of(f0 + f), hd_pitch, (uint8_t*)sl.dst.p + f * dst_frame, dst_pitch,
-                                                 dst_row, job->out_h, cudaMemcpyDeviceToHost, c->s_d2h));
+                    VR180_CUDA(cudaMemcpy2DAsync(dst_of(f0 + f), hd_pitch, d_out + f * out_frame, out_pitch,
+                                                 out_row, job->out_h, cudaMemcpyDeviceToHost, c->s_d2h));
             }
         }
         VR180_CUDA(cudaEventRecord(sl.ev_d2h, c->s_d2h));
@@ -575,7 +587,8 @@ int vr180_ctx_run(vr180_ctx_t* c, const vr180_host_job_t* job) {
     }
     for (int f = 0; job->dst_frames && f < F; ++f)
         if (!job->dst_frames[f]) return VR180_ERR_INVALID_ARG;
-    if ((size_t)job->dst_pitch < (size_t)job->out_w * V * C) return VR180_ERR_INVALID_ARG;
+    if (job->merge && (V != 2 || C != 3)) return VR180_ERR_INVALID_ARG;
+    if ((size_t)job->dst_pitch < (size_t)job->out_w * (job->merge ? 1 : V) * C) return VR180_ERR_INVALID_ARG;
     if (job->map_kind != VR180_MAPSRC_ANALYTIC && job->map_kind != VR180_MAPSRC_FLOAT2) return VR180_ERR_UNSUPPORTED;
     if (job->radius_mode == 1 && job->map_kind != VR180_MAPSRC_ANALYTIC) return VR180_ERR_UNSUPPORTED;
     if (job->staging < 0 || job->staging > 2 || job->copy_threads < 0) return VR180_ERR_INVALID_ARG;

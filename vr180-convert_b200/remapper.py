@@ -292,6 +292,7 @@ def warp_host(
     border_value: Any,
     auto_radius: bool = False,
     threshold: float = 10,
+    merge: bool = False,
 ) -> "NDArray[np.uint8] | list[NDArray[np.uint8]]":
     """ONE host job (vr180_ctx_run) for a whole batch.
 
@@ -301,7 +302,10 @@ def warp_host(
     single images and a list of arrays (one per frame) for lists.
 
     `auto_radius`: per-frame radius = max over the frame's views of get_radius (remapper.py:82-84 for one pair),
-    scanned and consumed on the device; a frame without a transition raises IndexError like the reference."""
+    scanned and consumed on the device; a frame without a transition raises IndexError like the reference.
+
+    `merge` (two views, 3 channels): the frames that come back are the anaglyph of the two eyes (H, W, 3), computed by
+    vr180_anaglyph on the device SBS frame (remapper.py:485-498) -- the SBS frame itself never leaves the GPU."""
     lib = N.lib()
     batched = isinstance(images[0], (list, tuple))
     frames = [[_as_image(im) for im in (v if batched else [v])] for v in images]
@@ -318,7 +322,9 @@ def warp_host(
     w, h = int(size_output[0]), int(size_output[1])
     first = np.asarray(images[0][0] if batched else images[0])
     squeeze = first.ndim == 2
-    outs = [_result_empty((h, w * n_views, ch)) for _ in range(n_frames)]
+    if merge and (n_views != 2 or ch != 3):
+        raise ValueError("merge needs two 3-channel views")
+    outs = [_result_empty((h, w * (1 if merge else n_views), ch)) for _ in range(n_frames)]
 
     job = N.HostJob()
     job.n_views, job.n_frames = n_views, n_frames
@@ -364,6 +370,7 @@ def warp_host(
     job.dst_frames = dptrs
     job.dst_pitch = outs[0].strides[0]
     job.dst_frame_stride = outs[0].strides[0] * h
+    job.merge = 1 if merge else 0
     trans = None
     if auto_radius:
         job.radius_mode = 1
@@ -473,19 +480,19 @@ def remap_maps(img: NDArray, xmap: NDArray, ymap: NDArray, *, interpolation: int
     return dst[:, :, 0] if np.asarray(img).ndim == 2 else dst
 
 
-def _anaglyph(images: Sequence[NDArray]) -> NDArray:
-    """`merge=True` branch of apply_lr (remapper.py:485-516): float64 channel-mean tint + "L"/"R" labels.
-    Calibration aid outside the hot path; host NumPy, cv2 only for putText."""
+def _anaglyph_labels(combine: NDArray[np.uint8]) -> NDArray[np.uint8]:
+    """The "L" / "R" labels of apply_lr(merge=True) (remapper.py:499-516).  The reference draws them with cv.putText on
+    its FLOAT64 image, where OpenCV has no anti-aliasing: pure (0, 128, 255) / (255, 128, 0) pixels with the LINE_8
+    raster, which cv.imwrite then stores unchanged -- so drawing with LINE_8 on the uint8 result of vr180_anaglyph is
+    the same picture.  (Font scale len(combine) // 1000: nothing is drawn below 1000 rows.)  cv2 only draws text here."""
     import cv2 as cv
 
     colors = [(0, 128, 255), (255, 128, 0)]
-    combine = sum(np.mean(im, axis=-1)[..., None] * np.array(col).reshape([1] * (im.ndim - 1) + [3])
-                  for im, col in zip(images, colors))
-    combine = combine / 255
+    combine = np.ascontiguousarray(combine)
     cv.putText(combine, "L", (0, len(combine[1]) // 10), cv.FONT_HERSHEY_SIMPLEX, len(combine) // 1000, colors[0], 2,
-               cv.LINE_AA)
+               cv.LINE_8)
     cv.putText(combine, "R", (len(combine[1]) // 2, len(combine[0]) // 10), cv.FONT_HERSHEY_SIMPLEX,
-               len(combine) // 1000, colors[1], 2, cv.LINE_AA)
+               len(combine) // 1000, colors[1], 2, cv.LINE_8)
     return combine
 
 
@@ -505,10 +512,9 @@ def apply_lr(
     """Stereo pair -> side-by-side frame written to `out_path` (remapper.py:406-520).  Both eyes are warped by
     one kernel launch that writes each eye into its half of the SBS frame (no separate concatenate)."""
     sbs = lr_frame(transformer, left_path, right_path, size_output=size_output, interpolation=interpolation,
-                   boarder_mode=boarder_mode, boarder_value=boarder_value, radius=radius)
+                   boarder_mode=boarder_mode, boarder_value=boarder_value, radius=radius, merge=merge)
     if merge:
-        w = int(size_output[0])
-        sbs = _anaglyph([sbs[:, :w], sbs[:, w:]])
+        sbs = _anaglyph_labels(sbs)
     _imwrite(out_path, sbs)
     LOG.info(f"Saved to {Path(out_path).absolute()}")
 
@@ -521,28 +527,49 @@ def _split_if_same_path(left, right):
 
 
 def lr_frame(transformer, left, right, *, size_output=(2048, 2048), interpolation=INTER_LANCZOS4,
-             boarder_mode=BORDER_CONSTANT, boarder_value=0, radius="auto") -> NDArray[np.uint8]:
-    """The in-memory part of apply_lr: returns the (H, 2W, C) SBS frame."""
+             boarder_mode=BORDER_CONSTANT, boarder_value=0, radius="auto", merge=False) -> NDArray[np.uint8]:
+    """The in-memory part of apply_lr: returns the (H, 2W, C) SBS frame, or with merge=True the (H, W, 3) anaglyph of
+    the two eyes without its text labels (remapper.py:485-498)."""
     interpolation, border_mode = _check_modes(interpolation, boarder_mode)
     left, right = _split_if_same_path(left, right)
     eyes = [_imread(p) if isinstance(p, (str, Path)) else p for p in (left, right)]
     kw = dict(size_output=size_output, interpolation=interpolation, border_mode=border_mode, border_value=boarder_value)
     same_shape = np.asarray(eyes[0]).shape == np.asarray(eyes[1]).shape
+    fused_merge = merge and same_shape and np.asarray(eyes[0]).ndim == 3 and np.asarray(eyes[0]).shape[2] == 3
+
+    def finish(halves):  # eyes that had to be warped separately
+        if merge:
+            return _merge_device(halves[0], halves[1])
+        return np.concatenate(halves, axis=1)
+
     if isinstance(transformer, tuple):  # per-eye transformer: own radius and own map per eye (remapper.py:460-473)
         radii = [get_radius_smart(radius, [eye]) for eye in eyes]
-        if same_shape:
-            return warp_host(list(transformer), eyes, radii=radii, share_map=False, **kw)
+        if same_shape and (fused_merge or not merge):
+            return warp_host(list(transformer), eyes, radii=radii, share_map=False, merge=fused_merge, **kw)
         # eyes of different geometry (unequal crops): the reference runs apply() per eye with that eye's size_input
-        halves = [warp_host([t], [eye], radii=[r], share_map=True, **kw) for t, eye, r in zip(transformer, eyes, radii)]
-        return np.concatenate(halves, axis=1)
+        return finish([warp_host([t], [eye], radii=[r], share_map=True, **kw) for t, eye, r in zip(transformer, eyes, radii)])
     radius_ = get_radius_smart(radius, eyes)  # one radius = max over both eyes, ONE map (remapper.py:475-484)
-    if same_shape:
-        return warp_host([transformer], eyes, radii=[radius_], share_map=True, **kw)
+    if same_shape and (fused_merge or not merge):
+        return warp_host([transformer], eyes, radii=[radius_], share_map=True, merge=fused_merge, **kw)
     # the reference builds the map from the LEFT image's shape and samples the right image with it (remapper.py:385)
     size_in = (np.asarray(eyes[0]).shape[0], np.asarray(eyes[0]).shape[1])
-    halves = [_warp_with_first_geometry(transformer, eye, size_in, radius_, size_output, interpolation, border_mode,
-                                        boarder_value) for eye in eyes]
-    return np.concatenate(halves, axis=1)
+    return finish([_warp_with_first_geometry(transformer, eye, size_in, radius_, size_output, interpolation, border_mode,
+                                             boarder_value) for eye in eyes])
+
+
+def _merge_device(left: NDArray, right: NDArray) -> NDArray[np.uint8]:
+    """vr180_anaglyph on two already-warped eyes (the rare paths where they could not share one job)."""
+    import torch
+
+    if left.shape != right.shape or left.ndim != 3 or left.shape[2] != 3:
+        raise ValueError("anaglyph merge needs two 3-channel images of equal shape")
+    dev = torch.device("cuda", _default_device)
+    h, w = left.shape[:2]
+    sbs = torch.from_numpy(np.concatenate([left, right], axis=1)).to(dev)
+    out = torch.empty((h, w, 3), dtype=torch.uint8, device=dev)
+    N.check(N.lib().vr180_anaglyph(sbs.data_ptr(), sbs.stride(0), 0, w, h, 1, out.data_ptr(), out.stride(0), 0,
+                                   torch.cuda.current_stream(dev).cuda_stream), "vr180_anaglyph")
+    return out.cpu().numpy()
 
 
 def lr_frames(transformer, lefts: Sequence[Any], rights: Sequence[Any], *, size_output=(2048, 2048),
@@ -575,3 +602,47 @@ def lr_frames(transformer, lefts: Sequence[Any], rights: Sequence[Any], *, size_
         return warp_host(ts, [lefts, rights], radii=[1.0] * len(ts), share_map=not per_eye, auto_radius=True, **kw)
     radius_ = get_radius_smart(radius, [lefts[0], rights[0]])  # "max" / a number: the same for every pair
     return warp_host(ts, [lefts, rights], radii=[radius_] * len(ts), share_map=not per_eye, **kw)
+
+
+def match_lr(
+    decoder: TransformerBase | tuple[TransformerBase, TransformerBase],
+    points_l: Sequence[tuple[float, float]],
+    points_r: Sequence[tuple[float, float]],
+    in_paths: Sequence[Path | str | NDArray],
+    *,
+    radius: float | Literal["auto", "max"] = "auto",
+) -> tuple[NDArray, NDArray]:
+    """Matched pixel positions of the two eyes -> unit vectors, the arguments of rotation_match() (remapper.py:251-321):
+    (decoder * Denormalize(scale=(r, r), center)).inverse_transform on the points, then equidistant_to_3d.  All points
+    of the call go through ONE vr180_transform_points launch per decoder (float64 on the device; the reference runs
+    the same chain in float32 NumPy, so results agree to float32 rounding).  `in_paths` may hold arrays as well."""
+    import torch
+
+    if len(points_l) != len(points_r):
+        raise ValueError("The number of points must be the same.")
+    images = [_imread(p) if isinstance(p, (str, Path)) else p for p in in_paths]
+    center = (images[0].shape[1] // 2, images[0].shape[0] // 2)
+    radius_ = get_radius_smart(radius, images)
+    dev = torch.device("cuda", _default_device)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def to_3d(dec: TransformerBase, pts) -> NDArray:
+        pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2).astype(np.float32).astype(np.float64)  # :295, :309
+        chain_t = dec * DenormalizeTransformer(scale=(radius_, radius_), center=center)
+        ops = chain_t.lower(inverse=True)
+        if ops is None or len(ops) > N.MAX_OPS:  # user-defined decoder: its own NumPy code
+            from .transformer import equidistant_to_3d
+
+            x, y = chain_t.inverse_transform(pts[:, 0], pts[:, 1])
+            return equidistant_to_3d(x, y)
+        chain = N.make_chain(ops)
+        xy = torch.from_numpy(np.ascontiguousarray(pts.T)).to(dev)
+        v3 = torch.empty((pts.shape[0], 3), dtype=torch.float64, device=dev)
+        N.check(N.lib().vr180_transform_points(C.byref(chain), pts.shape[0], xy[0].data_ptr(), xy[1].data_ptr(), None,
+                                               None, v3.data_ptr(), stream), "vr180_transform_points")
+        return v3.cpu().numpy()
+
+    if isinstance(decoder, tuple):
+        return to_3d(decoder[0], points_l), to_3d(decoder[1], points_r)
+    v = to_3d(decoder, np.concatenate([np.asarray(points_l).reshape(-1, 2), np.asarray(points_r).reshape(-1, 2)], axis=0))
+    return v[: len(points_l)], v[len(points_l):]
