@@ -46,6 +46,9 @@ WORKLOADS = {
     "8k_rot_poly_linear": dict(n=4096, interp=1, tuple_=True, chain="rot_poly", src="analytic", radius="fixed", pairs=64,
                                desc="batched 8K stereo pairs (2x4096^2 -> 8192x4096), per-eye Euclidean3DRotator+"
                                     "PolynomialScaler, fused analytic warp, INTER_LINEAR [BASELINE configs[2], batched]"),
+    "8k_rot_poly_lut": dict(n=4096, interp=1, tuple_=True, chain="rot_poly", src="lut_packed", radius="fixed", pairs=64,
+                            desc="the headline workload with the coordinates cached in two tile-packed LUTs (built once, "
+                                 "outside the timed region) instead of being re-evaluated by every launch: the video-loop path"),
     "4k_pair_linear": dict(n=2048, interp=1, tuple_=False, chain="base", src="analytic", radius="fixed", pairs=1,
                            desc="single 4K pair (2x2048^2 -> 4096x2048), base chain, fused analytic, INTER_LINEAR "
                                 "[BASELINE configs[1]]; a ring of pairs larger than L2 is cycled"),

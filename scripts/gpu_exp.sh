@@ -4,7 +4,7 @@ TAG=$1; shift
 mkdir -p gpurun_out
 i=0
 for A in "$@"; do
-  timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --no-other-workloads $A > gpurun_out/${TAG}_exp$i.json 2>> gpurun_out/${TAG}_exp.err
+  timeout 300 python bench.py --steps ${STEPS:-10} --warmup 3 --no-e2e --no-cpu-baseline --no-other-workloads $A > gpurun_out/${TAG}_exp$i.json 2>> gpurun_out/${TAG}_exp.err
   python - <<PY
 import json
 try:

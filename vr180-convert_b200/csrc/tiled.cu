@@ -47,6 +47,7 @@
 
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "chain.cuh"
@@ -700,9 +701,15 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     }
 }
 
+// CTAs per SM the kernel is compiled for: 4 (56 registers) unless the mode asks for fewer, larger CTAs
+template <class M, class = void>
+struct MinCtas { static constexpr int value = 4; };
+template <class M>
+struct MinCtas<M, std::void_t<decltype(M::kMinCtas)>> { static constexpr int value = M::kMinCtas; };
+
 // DYN: per-frame radius from device memory (vr180_mapsrc_t::radius_dev); FR: frames per pipeline item
 template <class M, bool DYN, int FR>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, MinCtas<M>::value)
 k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_chain_t chain0,
              const __grid_constant__ vr180_chain_t chain1, const __grid_constant__ TiledParams tp,
              const __grid_constant__ TmaMaps tm) {
