@@ -606,3 +606,30 @@ def test_match_lr_matches_reference_golden(golden_merge_match, golden_apply):
     np.testing.assert_allclose(vr, g["match/tuple/70.0/vr"], rtol=0, atol=3e-6, equal_nan=True)
     with pytest.raises(ValueError):
         V.match_lr(dec, pts_l[:3], pts_r, imgs, radius=50.0)
+
+
+@pytest.mark.parametrize("interp", [1, 4])
+def test_host_pipeline_output_width_not_16_byte_aligned(interp):
+    """--size 1000x1000-style outputs (W * 3 not a multiple of 16 bytes): the host pipeline puts the right eye at a
+    16-byte aligned column of its device frame (so the launch stays on the TMA-tiled kernel) and downloads the eyes as
+    two column segments into the dense host frame; pinned and pageable destinations, SBS and merged output."""
+    hin, win, wout, hout = 160, 160, 100, 72  # 300 bytes per eye row: 12 mod 16
+    t = V.EquirectangularEncoder() * V.PolynomialScaler([0, 1, 0.03]) * V.FisheyeDecoder("equidistant")
+    lefts = [disc_frame(hin, win, seed=i) for i in range(5)]
+    rights = [disc_frame(hin, win, seed=50 + i) for i in range(5)]
+    xm, ym = chain_np.get_map([("equirect_enc", True), ("poly", [0, 1, 0.03]), ("fisheye_dec", "equidistant")], radius=80.0,
+                              size_input=(hin, win), size_output=(wout, hout))
+    got = V.lr_frames(t, lefts, rights, size_output=(wout, hout), interpolation=interp, radius=80.0)
+    import os
+    os.environ["VR180_PINNED_OUTPUTS"] = "0"  # pageable result arrays: the staged (drain thread) download path
+    try:
+        got_pageable = V.lr_frames(t, lefts, rights, size_output=(wout, hout), interpolation=interp, radius=80.0)
+    finally:
+        del os.environ["VR180_PINNED_OUTPUTS"]
+    for f in range(5):
+        eyes = [cv2.remap(img, xm, ym, interpolation=interp) for img in (lefts[f], rights[f])]
+        want = np.concatenate(eyes, axis=1)
+        assert got[f].shape == (hout, 2 * wout, 3) and np.array_equal(got[f], want), (interp, f)
+        assert np.array_equal(got_pageable[f], want), (interp, f, "pageable")
+        merged = V.lr_frame(t, lefts[f], rights[f], size_output=(wout, hout), interpolation=interp, radius=80.0, merge=True)
+        assert np.array_equal(merged, remap_np.anaglyph_u8(eyes[0], eyes[1])), (interp, f, "merge")

@@ -132,8 +132,8 @@ int vr180_anaglyph(const uint8_t* sbs_dev, int64_t sbs_pitch, int64_t sbs_frame_
         return VR180_ERR_INVALID_ARG;
     DeviceGuard g(out_dev);
     if (!g.ok) return VR180_ERR_INVALID_ARG;
-    return launch_anaglyph(sbs_dev, sbs_pitch, sbs_frame_stride, eye_w, h, n_frames, out_dev, out_pitch, out_frame_stride,
-                           (cudaStream_t)stream);
+    return launch_anaglyph(sbs_dev, sbs_pitch, sbs_frame_stride, eye_w, eye_w, h, n_frames, out_dev, out_pitch,
+                           out_frame_stride, (cudaStream_t)stream);
 }
 
 int vr180_transform_points(const vr180_chain_t* chain, int64_t n, const double* x_dev, const double* y_dev,

@@ -96,8 +96,8 @@ int launch_remap_tiled(const RemapArgs& a, int channels, int interp, const vr180
 int launch_get_radius(const vr180_image_t* views, int n_views, int n_frames, double threshold, int32_t* transitions,
                       double* radius, cudaStream_t st);
 int validate_chain(const vr180_chain_t* c);
-int launch_anaglyph(const uint8_t* sbs, int64_t pitch, int64_t frame_stride, int W, int H, int n_frames, uint8_t* out,
-                    int64_t out_pitch, int64_t out_frame_stride, cudaStream_t st);
+int launch_anaglyph(const uint8_t* sbs, int64_t pitch, int64_t frame_stride, int W, int right_col, int H, int n_frames,
+                    uint8_t* out, int64_t out_pitch, int64_t out_frame_stride, cudaStream_t st);  // right eye at column right_col
 int launch_transform_points(const vr180_chain_t* chain, long long n, const double* x, const double* y, double* ox,
                             double* oy, double* v3, cudaStream_t st);
 

@@ -401,14 +401,14 @@ int launch_get_radius(const vr180_image_t* views, int n_views, int n_frames, dou
 // combine = mean_c(L)[..., None] * (0, 128, 255) + mean_c(R)[..., None] * (255, 128, 0);  combine /= 255   (float64,
 // one rounding per NumPy ufunc), then cv.imwrite's float64 -> uint8 conversion (round half to even, saturate).
 __global__ void __launch_bounds__(256) k_anaglyph(const uint8_t* __restrict__ sbs, long long pitch, long long frame_stride,
-                                                  int W, int H, uint8_t* __restrict__ out, long long out_pitch,
-                                                  long long out_frame_stride) {
+                                                  int W, int right_col, int H, uint8_t* __restrict__ out,
+                                                  long long out_pitch, long long out_frame_stride) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (i >= W) return;
     const uint8_t* row = sbs + (long long)blockIdx.z * frame_stride + (long long)j * pitch;
     const uint8_t* l = row + (long long)i * 3;
-    const uint8_t* r = row + (long long)(W + i) * 3;
+    const uint8_t* r = row + (long long)(right_col + i) * 3;
     const double ml = __ddiv_rn((double)(__ldg(l) + __ldg(l + 1) + __ldg(l + 2)), 3.0);  // np.mean(axis=-1)
     const double mr = __ddiv_rn((double)(__ldg(r) + __ldg(r + 1) + __ldg(r + 2)), 3.0);
     const double cl[3] = {0.0, 128.0, 255.0}, cr[3] = {255.0, 128.0, 0.0};
@@ -420,12 +420,12 @@ __global__ void __launch_bounds__(256) k_anaglyph(const uint8_t* __restrict__ sb
     }
 }
 
-int launch_anaglyph(const uint8_t* sbs, int64_t pitch, int64_t frame_stride, int W, int H, int n_frames, uint8_t* out,
-                    int64_t out_pitch, int64_t out_frame_stride, cudaStream_t st) {
+int launch_anaglyph(const uint8_t* sbs, int64_t pitch, int64_t frame_stride, int W, int right_col, int H, int n_frames,
+                    uint8_t* out, int64_t out_pitch, int64_t out_frame_stride, cudaStream_t st) {
     if (n_frames == 0) return VR180_OK;
     if (H > 65535 || n_frames > 65535) return VR180_ERR_UNSUPPORTED;
     dim3 grid((W + 255) / 256, H, n_frames);
-    k_anaglyph<<<grid, 256, 0, st>>>(sbs, pitch, frame_stride, W, H, out, out_pitch, out_frame_stride);
+    k_anaglyph<<<grid, 256, 0, st>>>(sbs, pitch, frame_stride, W, right_col, H, out, out_pitch, out_frame_stride);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     VR180_CUDA(cudaGetLastError());
     return VR180_OK;

@@ -360,12 +360,24 @@ static int ctx_run_locked(vr180_ctx* c, const vr180_host_job_t* job) {
     const bool scattered = job->src_frames[0] != nullptr;
     const size_t src_row = (size_t)job->src_cols * C, src_pitch = align_up(src_row, 16);
     const size_t src_frame = src_pitch * job->src_rows;
-    const size_t dst_row = (size_t)job->out_w * V * C, dst_pitch = align_up(dst_row, 16);
+    // Device SBS frame: eye 1 starts at a 16-byte aligned column (a TMA box must start at a 16-byte aligned address;
+    // --size 1000x1000 would otherwise push the whole launch to the per-pixel kernel).  The host frame stays dense:
+    // the two eyes are then downloaded as two column segments.
+    const size_t eye1_col = (V == 2 && ((size_t)job->out_w * C) % 16 != 0) ? align_up((size_t)job->out_w, 16) : (size_t)job->out_w;
+    const size_t dst_row = (V == 2 ? eye1_col + job->out_w : (size_t)job->out_w) * C, dst_pitch = align_up(dst_row, 16);
     const size_t dst_frame = dst_pitch * job->out_h;
     // what goes back to the host: the SBS frame, or (merge) the anaglyph of its two halves
     const bool merge = job->merge != 0;
     const size_t out_row = merge ? (size_t)job->out_w * C : dst_row, out_pitch = align_up(out_row, 16);
     const size_t out_frame = out_pitch * job->out_h;
+    struct Seg { size_t dev_col, host_col, bytes; };  // column segments (bytes) of a device row that go to the host row
+    std::vector<Seg> segs;
+    if (!merge && V == 2 && eye1_col != (size_t)job->out_w) {
+        segs.push_back({0, 0, (size_t)job->out_w * C});
+        segs.push_back({eye1_col * C, (size_t)job->out_w * C, (size_t)job->out_w * C});
+    } else {
+        segs.push_back({0, 0, merge ? out_row : (size_t)job->out_w * V * C});
+    }
 
     auto src_of = [&](int v, int f) -> const uint8_t* {
         return scattered ? job->src_frames[v][f] : job->src[v] + (size_t)f * job->src_frame_stride[v];
@@ -499,7 +511,7 @@ static int ctx_run_locked(vr180_ctx* c, const vr180_host_job_t* job) {
             vw.src.channels = C;
             vw.src.pitch = (int64_t)src_pitch;
             vw.src.frame_stride = (int64_t)src_frame;
-            vw.dst_x_offset = v * job->out_w;
+            vw.dst_x_offset = v ? (int)eye1_col : 0;
             const int m = (n_maps == 2) ? v : 0;
             vw.map.kind = job->map_kind;
             if (job->map_kind == VR180_MAPSRC_ANALYTIC) {
@@ -519,8 +531,8 @@ static int ctx_run_locked(vr180_ctx* c, const vr180_host_job_t* job) {
         rc = launch_remap(&p, c->s_comp);
         if (rc != VR180_OK) return rc;
         if (merge) {
-            rc = launch_anaglyph((const uint8_t*)sl.dst.p, (int64_t)dst_pitch, (int64_t)dst_frame, job->out_w, job->out_h, nf,
-                                 (uint8_t*)sl.merged.p, (int64_t)out_pitch, (int64_t)out_frame, c->s_comp);
+            rc = launch_anaglyph((const uint8_t*)sl.dst.p, (int64_t)dst_pitch, (int64_t)dst_frame, job->out_w, (int)eye1_col,
+                                 job->out_h, nf, (uint8_t*)sl.merged.p, (int64_t)out_pitch, (int64_t)out_frame, c->s_comp);
             if (rc != VR180_OK) return rc;
         }
         const uint8_t* d_out = (const uint8_t*)(merge ? sl.merged.p : sl.dst.p);
@@ -533,8 +545,9 @@ static int ctx_run_locked(vr180_ctx* c, const vr180_host_job_t* job) {
             VR180_CUDA(cudaEventRecord(sl.ev_d2h, c->s_d2h));
             std::vector<Copy2D> cp;
             for (int f = 0; f < nf; ++f)
-                cp.push_back({dst_of(f0 + f), (const uint8_t*)sl.h_dst.p + (size_t)f * out_frame, (size_t)job->dst_pitch,
-                              out_pitch, out_row, (size_t)job->out_h});
+                for (const Seg& g : segs)
+                    cp.push_back({dst_of(f0 + f) + g.host_col, (const uint8_t*)sl.h_dst.p + (size_t)f * out_frame + g.dev_col,
+                                  (size_t)job->dst_pitch, out_pitch, g.bytes, (size_t)job->out_h});
             cudaEvent_t ev = sl.ev_d2h;
             slot_ticket[s] = c->push_drain([pool, ev, cp] {
                 cudaEventSynchronize(ev);
@@ -544,19 +557,21 @@ static int ctx_run_locked(vr180_ctx* c, const vr180_host_job_t* job) {
         }
         const size_t hd_pitch = (size_t)job->dst_pitch;
         const bool dense_out = !job->dst_frames && (size_t)job->dst_frame_stride == hd_pitch * job->out_h;
-        if (dense_out && hd_pitch == out_pitch) {
+        if (dense_out && hd_pitch == out_pitch && segs.size() == 1) {
             VR180_CUDA(cudaMemcpyAsync(dst_of(f0), d_out, out_frame * nf, cudaMemcpyDeviceToHost, c->s_d2h));
         } else if (dense_out) {
-            VR180_CUDA(cudaMemcpy2DAsync(dst_of(f0), hd_pitch, d_out, out_pitch, out_row, (size_t)job->out_h * nf,
-                                         cudaMemcpyDeviceToHost, c->s_d2h));
+            for (const Seg& g : segs)
+                VR180_CUDA(cudaMemcpy2DAsync(dst_of(f0) + g.host_col, hd_pitch, d_out + g.dev_col, out_pitch, g.bytes,
+                                             (size_t)job->out_h * nf, cudaMemcpyDeviceToHost, c->s_d2h));
         } else {
             for (int f = 0; f < nf; ++f) {
-                if (hd_pitch == out_pitch)
-                    VR180_CUDA(cudaMemcpyAsync(dst_of(f0 + f), d_out + f * out_frame, out_frame,
-                                               cudaMemcpyDeviceToHost, c->s_d2h));
+                if (hd_pitch == out_pitch && segs.size() == 1)
+                    VR180_CUDA(cudaMemcpyAsync(dst_of(f0 + f), d_out + f * out_frame, out_frame, cudaMemcpyDeviceToHost,
+                                               c->s_d2h));
                 else
-                    VR180_CUDA(cudaMemcpy2DAsync(dst_of(f0 + f), hd_pitch, d_out + f * out_frame, out_pitch,
-                                                 out_row, job->out_h, cudaMemcpyDeviceToHost, c->s_d2h));
+                    for (const Seg& g : segs)
+                        VR180_CUDA(cudaMemcpy2DAsync(dst_of(f0 + f) + g.host_col, hd_pitch, d_out + f * out_frame + g.dev_col,
+                                                     out_pitch, g.bytes, job->out_h, cudaMemcpyDeviceToHost, c->s_d2h));
             }
         }
         VR180_CUDA(cudaEventRecord(sl.ev_d2h, c->s_d2h));
