@@ -253,6 +253,24 @@ int vr180_transform_points(const vr180_chain_t* chain, int64_t n, const double* 
                            double* out_x_dev, double* out_y_dev, double* out_v3_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * (6) optional codec offload (nvJPEG, loaded with dlopen at first use) -- stands in for cv.imread / cv.imwrite around
+ *     the hot path (remapper.py:373, :453, :519) so that a JPEG -> warp -> JPEG conversion moves only compressed bytes
+ *     over PCIe.  OPT-IN: nvJPEG's decoder is not bit-compatible with the libjpeg-turbo decoder inside cv.imread (a few
+ *     grey levels on some pixels), so the default file path keeps cv2 and its bit-exact contract.
+ *     vr180_jpeg_available: 1 when libnvjpeg could be loaded.  vr180_jpeg_decode: host JPEG bytes -> interleaved BGR
+ *     uint8 on the device (the layout cv.imread returns; width / height from vr180_jpeg_info).  vr180_jpeg_encode:
+ *     interleaved BGR on the device -> host JPEG bytes with cv.imwrite's defaults (4:2:0, standard Huffman tables);
+ *     *out_len is the capacity on entry and the stream length on return (VR180_ERR_NOMEM + needed size if too small).
+ *     All entry points return VR180_ERR_UNSUPPORTED when libnvjpeg is absent.
+ * ---------------------------------------------------------------------------------------------------- */
+int vr180_jpeg_available(void);
+int vr180_jpeg_info(const uint8_t* jpeg_host, size_t n, int* width, int* height, int* channels);
+int vr180_jpeg_decode(const uint8_t* jpeg_host, size_t n, uint8_t* bgr_dev, int64_t pitch, int width, int height,
+                      void* stream);
+int vr180_jpeg_encode(const uint8_t* bgr_dev, int64_t pitch, int width, int height, int quality, uint8_t* out_host,
+                      size_t* out_len, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * Host-buffer pipeline (what the Python `apply` / `apply_lr` call with NumPy arrays): a context owns device
  * staging buffers and three streams (H2D, compute, D2H) and runs upload -> [get_radius] -> warp -> download
  * for a batch of frames with the copies of neighbouring frames overlapped.

@@ -633,3 +633,44 @@ def test_host_pipeline_output_width_not_16_byte_aligned(interp):
         assert np.array_equal(got_pageable[f], want), (interp, f, "pageable")
         merged = V.lr_frame(t, lefts[f], rights[f], size_output=(wout, hout), interpolation=interp, radius=80.0, merge=True)
         assert np.array_equal(merged, remap_np.anaglyph_u8(eyes[0], eyes[1])), (interp, f, "merge")
+
+
+def test_nvjpeg_codec_path(tmp_path, golden_apply):
+    """Opt-in device codec (include/vr180_b200.h section 6): nvJPEG decode agrees with cv.imread up to the decoder
+    differences the header documents (NOT bit-exact: stated tolerance mean |diff| < 1.5 grey levels, < 1 % of the
+    samples off by more than 8), and the JPEG -> warp -> JPEG form of apply_lr on the device produces the same picture
+    as the cv2 path up to codec noise (PSNR > 30 dB).  The default codec stays cv2 (bit-exact tests above)."""
+    import torch
+
+    from vr180_convert_b200 import codec
+
+    if not codec.available():
+        pytest.skip("libnvjpeg could not be loaded")
+    card = np.ascontiguousarray(np.kron(golden_apply["card"], np.ones((2, 2, 1), np.uint8)))  # 512 x 512 test card
+    src = tmp_path / "sbs.jpg"
+    cv2.imwrite(str(src), card)
+    want = cv2.imread(str(src))
+    got = codec.decode_jpeg_device(src).cpu().numpy()
+    assert got.shape == want.shape
+    d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    assert d.mean() < 1.5 and (d > 8).mean() < 0.01, (float(d.mean()), int(d.max()))
+    # encode: round trip through cv2's decoder
+    enc = codec.encode_jpeg_device(torch.from_numpy(want).cuda())
+    back = cv2.imdecode(np.frombuffer(enc, np.uint8), cv2.IMREAD_COLOR)
+    mse = np.mean((back.astype(np.float64) - want.astype(np.float64)) ** 2)
+    assert back.shape == want.shape and 10 * np.log10(255.0 ** 2 / mse) > 30
+    # whole apply_lr on the device vs the cv2 path
+    t = V.EquirectangularEncoder() * V.PolynomialScaler([0, 1, 0.02]) * V.FisheyeDecoder("equidistant")
+    out_ref, out_dev = tmp_path / "ref.jpg", tmp_path / "dev.jpg"
+    V.apply_lr(t, left_path=src, right_path=src, out_path=out_ref, size_output=(256, 256), interpolation=1, radius="max")
+    V.set_codec("nvjpeg")
+    try:
+        V.apply_lr(t, left_path=src, right_path=src, out_path=out_dev, size_output=(256, 256), interpolation=1, radius="max")
+        V.apply_lr(t, left_path=src, right_path=src, out_path=tmp_path / "dev.png", size_output=(256, 256), interpolation=1,
+                   radius="auto", merge=True)
+    finally:
+        V.set_codec("cv2")
+    a, b = cv2.imread(str(out_ref)).astype(np.float64), cv2.imread(str(out_dev)).astype(np.float64)
+    assert a.shape == b.shape == (256, 512, 3)
+    assert 10 * np.log10(255.0 ** 2 / np.mean((a - b) ** 2)) > 30
+    assert cv2.imread(str(tmp_path / "dev.png")).shape == (256, 256, 3)

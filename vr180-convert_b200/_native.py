@@ -89,6 +89,11 @@ SYMBOLS = {
                                  C.c_int64, C.c_void_p]),
     "vr180_transform_points": (C.c_int, [C.POINTER(Chain), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
+    "vr180_jpeg_available": (C.c_int, []),
+    "vr180_jpeg_info": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vr180_jpeg_decode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "vr180_jpeg_encode": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.POINTER(C.c_size_t), C.c_void_p]),
     "vr180_get_radius": (C.c_int, [C.POINTER(Image), C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
     "vr180_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),

@@ -19,7 +19,7 @@ CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
 LIB = PKG / "libvr180_b200.so"
 OBJ_DIR = PKG / "build"
-SOURCES = ["kernels.cu", "tiled.cu", "api.cu", "pipeline.cu"]
+SOURCES = ["kernels.cu", "tiled.cu", "api.cu", "pipeline.cu", "codec.cu"]
 HEADERS = ["chain.cuh", "sampler.cuh", "tables.cuh", "common.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -66,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-cudart", "static",
+    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-cudart", "static", "-ldl",
            "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:

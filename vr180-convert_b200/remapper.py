@@ -28,6 +28,18 @@ LOG = getLogger(__name__)
 INTER_NEAREST, INTER_LINEAR, INTER_CUBIC, INTER_AREA, INTER_LANCZOS4 = 0, 1, 2, 3, 4
 BORDER_CONSTANT, BORDER_REPLICATE, BORDER_REFLECT, BORDER_WRAP, BORDER_REFLECT_101, BORDER_TRANSPARENT = 0, 1, 2, 3, 4, 5
 
+_codec = os.environ.get("VR180_CODEC", "cv2")
+
+
+def set_codec(name: str) -> None:
+    """"cv2" (default: files are read / written by OpenCV on the host, bit-identical to the reference) or "nvjpeg"
+    (opt-in: the JPEG -> warp -> JPEG form of apply_lr decodes, warps and encodes on the GPU, see codec.py)."""
+    global _codec
+    if name not in ("cv2", "nvjpeg"):
+        raise ValueError("codec must be 'cv2' or 'nvjpeg'")
+    _codec = name
+
+
 _ctx_lock = threading.Lock()
 _ctxs: dict[int, C.c_void_p] = {}
 _default_device = 0
@@ -511,12 +523,70 @@ def apply_lr(
 ) -> None:
     """Stereo pair -> side-by-side frame written to `out_path` (remapper.py:406-520).  Both eyes are warped by
     one kernel launch that writes each eye into its half of the SBS frame (no separate concatenate)."""
+    if _codec == "nvjpeg" and _lr_files_on_device(transformer, left_path, right_path, out_path, size_output, interpolation,
+                                                  boarder_mode, boarder_value, radius, merge):
+        LOG.info(f"Saved to {Path(out_path).absolute()}")
+        return
     sbs = lr_frame(transformer, left_path, right_path, size_output=size_output, interpolation=interpolation,
                    boarder_mode=boarder_mode, boarder_value=boarder_value, radius=radius, merge=merge)
     if merge:
         sbs = _anaglyph_labels(sbs)
     _imwrite(out_path, sbs)
     LOG.info(f"Saved to {Path(out_path).absolute()}")
+
+
+def _lr_files_on_device(transformer, left_path, right_path, out_path, size_output, interpolation, boarder_mode,
+                        boarder_value, radius, merge) -> bool:
+    """set_codec("nvjpeg"): JPEG inputs are decoded by nvJPEG into device memory, warped there (SbsWarper: the same
+    kernels as the host path) and -- for a .jpg output without merge -- encoded there, so only compressed bytes cross
+    PCIe (remapper.py:448-456 split, :460-484 radius / map rules, :518-519).  Returns False when the request is not of
+    that form (the caller then takes the cv2 path)."""
+    from . import codec
+    from .video import SbsWarper
+
+    if not (codec.is_jpeg_path(left_path) and codec.is_jpeg_path(right_path) and codec.available()):
+        return False
+    import torch
+
+    dev = torch.device("cuda", _default_device)
+    interpolation, border_mode = _check_modes(interpolation, boarder_mode)
+    with torch.cuda.device(dev):
+        if Path(left_path) == Path(right_path):  # one SBS source file: halves as views (remapper.py:448-456)
+            full = codec.decode_jpeg_device(left_path, dev)
+            half = full.shape[1] // 2
+            eyes = [full[:, :half], full[:, half:]]
+        else:
+            eyes = [codec.decode_jpeg_device(p, dev) for p in (left_path, right_path)]
+        if eyes[0].shape != eyes[1].shape:
+            return False
+        rows, cols = int(eyes[0].shape[0]), int(eyes[0].shape[1])
+        left, right = (e.unsqueeze(0) for e in eyes)
+        per_eye = isinstance(transformer, tuple)
+        plan_radius: Any = radius
+        if isinstance(radius, str) and radius == "auto":
+            probe = SbsWarper(transformer, size_input=(rows, cols), size_output=size_output, interpolation=interpolation,
+                              boarder_mode=border_mode, boarder_value=boarder_value, radius="auto", device=dev)
+            _, trans = probe.radius_per_frame(left, right)
+            trans = trans[0].cpu().numpy()  # (view, {first, last})
+            if (trans < 0).any():
+                raise IndexError("index 0 is out of bounds for axis 0 with size 0")
+            per_view = [(int(t[1]) - int(t[0])) / 2 for t in trans]
+            plan_radius = per_view if per_eye else max(per_view)  # remapper.py:460-473 / :82-84
+            LOG.info(f"Radius: {plan_radius}, strategy: auto, image shape: {tuple(eyes[0].shape)}")
+        wp = SbsWarper(transformer, size_input=(rows, cols), size_output=size_output, interpolation=interpolation,
+                       boarder_mode=border_mode, boarder_value=boarder_value, radius=plan_radius, device=dev)
+        sbs = wp(left, right)[0]
+        w = int(size_output[0])
+        if merge:
+            out = torch.empty((sbs.shape[0], w, 3), dtype=torch.uint8, device=dev)
+            N.check(N.lib().vr180_anaglyph(sbs.data_ptr(), sbs.stride(0), 0, w, int(sbs.shape[0]), 1, out.data_ptr(),
+                                           out.stride(0), 0, torch.cuda.current_stream(dev).cuda_stream), "vr180_anaglyph")
+            _imwrite(out_path, _anaglyph_labels(out.cpu().numpy()))
+        elif codec.is_jpeg_path(out_path):
+            Path(out_path).write_bytes(codec.encode_jpeg_device(sbs))
+        else:
+            _imwrite(out_path, sbs.cpu().numpy())
+    return True
 
 
 def _split_if_same_path(left, right):
