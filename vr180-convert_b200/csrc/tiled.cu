@@ -720,16 +720,12 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     int* s_red = reinterpret_cast<int*>(smem + Lay<M>::kOffRed);          // [8][4]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        const uint32_t bars = smem_u32(smem + Lay<M>::kOffBar);
-        for (int st = 0; st < kMaxStages; ++st) {
-            mbar_init(bars + st * 8, 1);                               // full: the producer + tx bytes
-            mbar_init(bars + (kMaxStages + st) * 8, kSamplers / 32);  // empty: one arrive per sampling warp
-        }
-        for (int o = 0; o < kOutBufs; ++o) {
-            mbar_init(bars + (2 * kMaxStages + o) * 8, kSamplers / 32);  // ofull: one arrive per sampling warp
-            mbar_init(bars + (2 * kMaxStages + kOutBufs + o) * 8, 1);    // oempty: the producer
-        }
+    if (tid < 2 * kMaxStages + 2 * kOutBufs) {  // one barrier per thread: a single-frame launch is latency bound, and one
+        const uint32_t bars = smem_u32(smem + Lay<M>::kOffBar);  // thread initialising all 24 kept the whole CTA waiting
+        // layout: full[kMaxStages] (1: the producer + tx bytes), empty[kMaxStages] (one arrive per sampling warp),
+        //         ofull[kOutBufs] (one arrive per sampling warp), oempty[kOutBufs] (1: the producer)
+        const bool by_warps = (tid >= kMaxStages && tid < 2 * kMaxStages + kOutBufs);
+        mbar_init(bars + tid * 8, by_warps ? kSamplers / 32 : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy (TMA)
     }
     int* const s_cost = reinterpret_cast<int*>(smem + Lay<M>::kOffCost);  // wavefront cost of each candidate pitch
@@ -747,6 +743,13 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     auto pcol = [&](int k) { return M::kRowPatch ? lx : lx + 8 * k; };
     auto prow = [&](int k) { return M::kRowPatch ? ly + k : ly; };
     const bool full_tile = (x0 + kTileW <= a.W) && (y0 + M::kTileH <= a.H);
+
+    // tile-packed LUT: the tile's header (every thread: the producer warp needs the rectangle too)
+    PackedHdr hdr;
+    hdr.mnx = hdr.mxx = hdr.mny = hdr.mxy = 0;
+    hdr.flags = hdr.pad = 0;
+    if (mv.map_kind != VR180_MAPSRC_ANALYTIC && mv.packed) hdr = packed_header(mv.packed, blockIdx.x);
+    const bool packed_tile = (hdr.flags & 1) != 0;  // CTA-uniform: coordinates and bounding box come from the packed LUT
 
     // ---- coordinates of this thread's pixels --------------------------------------------------------------
     int sx[kPx], sy[kPx];
@@ -845,9 +848,8 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         // Tile-packed LUT (vr180_pack_lut_tiles): 16-byte tile header + one uint32 per pixel in thread order, i.e. ONE
         // 128-bit (bilinear / nearest), 64-bit (bicubic) or 32-bit (Lanczos4) coalesced load per thread.
         bool unpacked = false;
-        if (mv.packed) {
-            const PackedHdr hdr = packed_header(mv.packed, blockIdx.x);
-            if (hdr.flags & 1) {
+        {
+            if (packed_tile) {
                 const uint32_t* ent = packed_entries(mv.packed, tp.n_tiles) + ((size_t)blockIdx.x * kSamplers + tid) * kPx;
                 uint32_t e[kPx];
                 if constexpr (kPx == 4) {
@@ -908,23 +910,25 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
 
     // ---- source rectangle of the tile ---------------------------------------------------------------------
     int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
+    if (!packed_tile) {  // a packed tile carries its bounding box in the header: no reduction
 #pragma unroll
-    for (int k = 0; k < kPx; ++k) {
-        const int ix = sat16(sx[k] >> M::kShift), iy = sat16(sy[k] >> M::kShift);
-        mnx = min(mnx, ix);
-        mxx = max(mxx, ix);
-        mny = min(mny, iy);
-        mxy = max(mxy, iy);
-    }
-    mnx = __reduce_min_sync(0xffffffffu, mnx);
-    mxx = __reduce_max_sync(0xffffffffu, mxx);
-    mny = __reduce_min_sync(0xffffffffu, mny);
-    mxy = __reduce_max_sync(0xffffffffu, mxy);
-    if (lane == 0 && sampler) {
-        s_red[warp * 4 + 0] = mnx;
-        s_red[warp * 4 + 1] = mxx;
-        s_red[warp * 4 + 2] = mny;
-        s_red[warp * 4 + 3] = mxy;
+        for (int k = 0; k < kPx; ++k) {
+            const int ix = sat16(sx[k] >> M::kShift), iy = sat16(sy[k] >> M::kShift);
+            mnx = min(mnx, ix);
+            mxx = max(mxx, ix);
+            mny = min(mny, iy);
+            mxy = max(mxy, iy);
+        }
+        mnx = __reduce_min_sync(0xffffffffu, mnx);
+        mxx = __reduce_max_sync(0xffffffffu, mxx);
+        mny = __reduce_min_sync(0xffffffffu, mny);
+        mxy = __reduce_max_sync(0xffffffffu, mxy);
+        if (lane == 0 && sampler) {
+            s_red[warp * 4 + 0] = mnx;
+            s_red[warp * 4 + 1] = mxx;
+            s_red[warp * 4 + 2] = mny;
+            s_red[warp * 4 + 3] = mxy;
+        }
     }
     DynRadius dr;
     dr.radius = nullptr;
@@ -959,14 +963,21 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         }
     }
     nan_px = __syncthreads_or(nan_px);
-    mnx = mny = INT_MAX;
-    mxx = mxy = INT_MIN;
+    if (packed_tile) {
+        mnx = hdr.mnx;
+        mxx = hdr.mxx;
+        mny = hdr.mny;
+        mxy = hdr.mxy;
+    } else {
+        mnx = mny = INT_MAX;
+        mxx = mxy = INT_MIN;
 #pragma unroll
-    for (int w = 0; w < kSamplers / 32; ++w) {
-        mnx = min(mnx, s_red[w * 4 + 0]);
-        mxx = max(mxx, s_red[w * 4 + 1]);
-        mny = min(mny, s_red[w * 4 + 2]);
-        mxy = max(mxy, s_red[w * 4 + 3]);
+        for (int w = 0; w < kSamplers / 32; ++w) {
+            mnx = min(mnx, s_red[w * 4 + 0]);
+            mxx = max(mxx, s_red[w * 4 + 1]);
+            mny = min(mny, s_red[w * 4 + 2]);
+            mxy = max(mxy, s_red[w * 4 + 3]);
+        }
     }
     // taps cover columns ix - kLo .. ix + kHi and rows iy - kLo .. iy + kHi
     const int bx0 = (3 * (mnx - M::kLo)) & ~15, bx1 = (3 * (mxx + M::kHi + 1) + 15) & ~15;  // 16-byte granules
