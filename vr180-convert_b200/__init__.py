@@ -6,7 +6,7 @@ entry points (`SbsWarper`, `shard_range`) used for video and multi-GPU runs.
 __version__ = "0.1.0"
 
 from .quat import from_euler_angles, from_rotation_vector, quaternion, rotate_vectors
-from .remapper import apply, apply_lr, get_map, get_radius_smart, lr_frame, lr_frames, match_lr, remap_maps, set_codec, set_device
+from .remapper import apply, apply_lr, get_map, get_radius_smart, lr_frame, lr_frames, match_lr, pinned_empty, remap_maps, set_codec, set_device
 from .transformer import (
     DenormalizeTransformer,
     EquirectangularDecoder,
@@ -34,7 +34,7 @@ __all__ = [
     "TransformerBase", "ZoomTransformer", "MultiTransformer", "NormalizeTransformer", "PolarRollTransformer",
     "DenormalizeTransformer", "FisheyeDecoder", "FisheyeEncoder", "EquirectangularEncoder", "EquirectangularDecoder",
     "Euclidean3DRotator", "Euclidean3DTransformer", "InverseTransformer", "PolynomialScaler", "RectilinearDecoder",
-    "apply", "apply_lr", "get_map", "get_radius", "get_radius_smart", "lr_frame", "lr_frames", "match_lr", "remap_maps", "set_codec", "set_device",
+    "apply", "apply_lr", "get_map", "get_radius", "get_radius_smart", "lr_frame", "lr_frames", "match_lr", "pinned_empty", "remap_maps", "set_codec", "set_device",
     "equidistant_to_3d", "equidistant_from_3d", "quaternion", "from_rotation_vector", "from_euler_angles",
     "rotate_vectors", "SbsWarper", "shard_range", "max_over_ranks", "gather_shards",
 ]

@@ -105,6 +105,13 @@ class _PinnedPool:
 _pinned = _PinnedPool()
 
 
+def pinned_empty(shape: tuple[int, ...]) -> NDArray[np.uint8]:
+    """A uint8 array in page-locked host memory (vr180_host_alloc), recycled when garbage-collected.  Frames a capture
+    or decode loop writes straight into such arrays are uploaded by DMA without the packing copy plain NumPy arrays
+    need (the host pipeline decides per buffer, include/vr180_b200.h `staging`)."""
+    return _pinned.empty(tuple(int(v) for v in shape))
+
+
 def _result_empty(shape: tuple[int, ...]) -> NDArray[np.uint8]:
     if os.environ.get("VR180_PINNED_OUTPUTS", "1") == "0":
         return np.empty(shape, dtype=np.uint8)
