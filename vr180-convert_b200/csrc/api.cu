@@ -13,6 +13,7 @@ std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_debug_frames_per_cta{0};
 std::atomic<int> g_debug_tiled_flags{-1};
 std::atomic<int> g_debug_max_frames_per_cta{0};
+std::atomic<int> g_debug_stream_grid{0};
 static thread_local std::string t_cuda_error;
 
 void set_cuda_error(cudaError_t e, const char* where) {
@@ -82,6 +83,7 @@ int vr180_debug_set(int what, int value) {
     if (what == 0) return g_debug_frames_per_cta.exchange(value < 0 ? 0 : value);
     if (what == 1) return g_debug_tiled_flags.exchange(value);
     if (what == 2) return g_debug_max_frames_per_cta.exchange(value < 0 ? 0 : value);
+    if (what == 3) return g_debug_stream_grid.exchange(value < 0 ? 0 : value);
     return VR180_ERR_INVALID_ARG;
 }
 

@@ -1,0 +1,310 @@
+// stream.cu -- the tiled warp for launches of ONE or a few frames: tiles streamed through persistent CTAs.
+//
+// Replaces cv.remap per eye + np.concatenate (/root/reference/src/vr180_convert/remapper.py:388-398, :518) for the
+// frame-at-a-time form of the path (a video loop calling apply_lr / lr_frame once per stereo pair with cached maps:
+// BASELINE configs[1], north_star (2) "cached-LUT path for repeated video frames").
+//
+// k_warp_tiled (tiled.cu) gives every CTA ONE tile and amortises the tile's prologue over the frames of a batch.  With
+// one frame per launch nothing is amortised and the CTA is a chain of latencies (header -> coordinates -> bounding box
+// -> TMA load -> sample -> TMA store), 100 instructions per 32 pixels and 41 us for a 4K pair (HBM time: 7 us).
+// Here a CTA is persistent and walks the tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  of the launch:
+//   * the coordinates come from the tile-packed LUT (vr180_pack_lut_tiles), whose 16-byte tile header carries the
+//     tile's bounding box: the producer warp needs nothing from the sampling warps to fetch a tile's source rectangle,
+//     so it runs up to kSlots items (tile, frame, eye) AHEAD of them -- the TMA loads of the next tiles are in flight
+//     while the current one is sampled;
+//   * the sampling warps prefetch the next tile's header and LUT entries (one 128-bit load per thread) before they
+//     sample the current one;
+//   * per tile a thread only unpacks its 4 entries into the sampling constants (offset, selectors, weights); no
+//     block-wide reduction, no pitch search, no per-launch-mode branches.
+// Pipeline, barriers and the sampling / re-packing of a tile are those of k_warp_tiled (tiled.cuh), with one frame of
+// one eye per item; the stage ring has fixed-size slots because consecutive items belong to different tiles.
+// Tiles that cannot be packed (partial edge tiles, NaN / huge coordinates), whose rectangle exceeds a slot, or that
+// touch the source edge under a non-zero border take the per-pixel gather, as in k_warp_tiled.
+#include "tiled.cuh"
+
+namespace vr180 {
+namespace tiled {
+
+constexpr int kSlots = 3;  // stage ring: slots of Lay<M>::kStageArea / 3 bytes (13.5 KB; a bilinear 8K tile needs <= 10.5 KB)
+
+template <class M>
+struct SLay {
+    static constexpr int kSlotBytes = (Lay<M>::kStageArea / kSlots) & ~127;
+    static constexpr int kOutTileBytes = M::kTileH * kTileW * 3;
+    static constexpr int kOB = kOutBufs;  // out buffers of one tile each
+    static constexpr int kOffOut = kSlots * kSlotBytes;
+    static constexpr int kOffBar = kOffOut + kOB * kOutTileBytes;  // full[kSlots], ofull[kOB], oempty[kOB]
+    static constexpr int kOffQ = (kOffBar + (kSlots + 2 * kOB) * 8 + 15) & ~15;  // int4 per slot: store coordinates of the item in it
+    static constexpr int kOffW = (kOffQ + kSlots * 16 + 15) & ~15;
+    static constexpr int kSmemBytes = kOffW + M::kWeightSmem;
+};
+
+struct StreamParams {
+    int tiles_x, n_tiles, n_units;  // units = map groups x tiles
+    int zero_border;
+    const short* tab;
+};
+
+// Source rectangle of a packed tile from its header alone (both the producer and the sampling warps evaluate it).
+struct UnitGeom {
+    int fast, bx0, ry0, pitch, rsel, rect_bytes;
+};
+template <class M>
+__device__ __forceinline__ UnitGeom unit_geom(const PackedHdr& h, int zero_border, int src_cols, int src_rows) {
+    UnitGeom g;
+    const int mnx = h.mnx, mxx = h.mxx, mny = h.mny, mxy = h.mxy;
+    g.bx0 = (3 * (mnx - M::kLo)) & ~15;
+    const int bx1 = (3 * (mxx + M::kHi + 1) + 15) & ~15;
+    g.ry0 = mny - M::kLo;
+    const int wbytes = bx1 - g.bx0, nrows = mxy + M::kHi + 1 - g.ry0;
+    g.pitch = max(wbytes, kPitchMin);
+    g.rsel = nrows <= M::kRowsMin ? 0 : (nrows - M::kRowsMin + kRowsStep - 1) / kRowsStep;
+    g.rect_bytes = (M::kRowsMin + g.rsel * kRowsStep) * g.pitch;
+    const bool inside = mnx - M::kLo >= 0 && mxx + M::kHi <= src_cols - 1 && mny - M::kLo >= 0 && mxy + M::kHi <= src_rows - 1;
+    g.fast = (h.flags & 1) && wbytes <= kPitchMax && g.rsel < kRowSizes && g.rect_bytes <= SLay<M>::kSlotBytes &&
+             (zero_border || inside);
+    return g;
+}
+
+template <class M>
+__global__ void __launch_bounds__(kThreads, 4)
+k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ StreamParams sp,
+              const __grid_constant__ TmaMaps tm) {
+    constexpr int kPx = M::kPx;
+    constexpr int kOB = SLay<M>::kOB, kOutTileBytes = SLay<M>::kOutTileBytes, kSlotBytes = SLay<M>::kSlotBytes;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t s_stage = smem_u32(smem), s_full = s_stage + SLay<M>::kOffBar;
+    const uint32_t s_ofull = s_full + kSlots * 8, s_oempty = s_ofull + kOB * 8, s_out = s_stage + SLay<M>::kOffOut;
+    int4* const s_q = reinterpret_cast<int4*>(smem + SLay<M>::kOffQ);
+    if (tid < kSlots + 2 * kOB) {
+        const bool by_warps = tid >= kSlots && tid < kSlots + kOB;  // ofull: one arrive per sampling warp
+        mbar_init(s_full + tid * 8, by_warps ? kSamplers / 32 : 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nv = a.share_map ? a.n_views : 1;
+    const int src_cols = a.view[0].cols, src_rows = a.view[0].rows;
+    const int stride = gridDim.x;
+
+    if (warp == kSamplers / 32) {  // ---- producer: one thread drives the TMA unit ----
+        if (lane != 0) return;
+        int n_load = 0, n_store = 0, l_slot = 0, s_slot = 0;
+        auto store_next = [&]() {  // the oldest item in flight: its tile is complete -> TMA store, slot and out buffer are free
+            const int o = n_store & (kOB - 1);
+            mbar_wait(s_ofull + o * 8, (uint32_t)(n_store / kOB) & 1u);
+            const int4 q = s_q[s_slot];
+            tma_store_3d(&tm.dst, q.x, q.y, q.z, s_out + o * kOutTileBytes);
+            bulk_commit();
+            bulk_wait_read<0>();
+            mbar_arrive(s_oempty + o * 8);
+            ++n_store;
+            if (++s_slot == kSlots) s_slot = 0;
+        };
+        int u = blockIdx.x;
+        PackedHdr hn;
+        if (u < sp.n_units) hn = packed_header(a.view[u / sp.n_tiles].packed, (unsigned)(u % sp.n_tiles));
+        for (; u < sp.n_units; u += stride) {
+            const PackedHdr hdr = hn;
+            const int un = u + stride;
+            if (un < sp.n_units) hn = packed_header(a.view[un / sp.n_tiles].packed, (unsigned)(un % sp.n_tiles));
+            const UnitGeom g = unit_geom<M>(hdr, sp.zero_border, src_cols, src_rows);
+            if (!g.fast) continue;
+            const int grp = u / sp.n_tiles, tile = u - grp * sp.n_tiles;
+            const int ty = tile / sp.tiles_x, tx = tile - ty * sp.tiles_x;
+            const CUtensorMap* const map0 = &tm.src[grp][(g.pitch - kPitchMin) / kPitchStep][g.rsel];
+            for (int f = 0; f < a.n_frames; ++f) {
+                for (int v = 0; v < nv; ++v) {
+                    if (n_load - n_store == kSlots) store_next();
+                    const uint32_t bar = s_full + l_slot * 8;
+                    s_q[l_slot] = make_int4((a.view[grp + v].dst_x_offset + tx * kTileW) * 3, ty * M::kTileH, f, 0);
+                    mbar_expect_tx(bar, (uint32_t)g.rect_bytes);
+                    tma_load_3d(s_stage + l_slot * kSlotBytes, map0 + v * (kWidths * kRowSizes), g.bx0, g.ry0, f, bar);
+                    ++n_load;
+                    if (++l_slot == kSlots) l_slot = 0;
+                }
+            }
+        }
+        while (n_store < n_load) store_next();
+        bulk_wait_read<0>();  // shared memory must stay valid until the last store has read it
+        return;
+    }
+
+    // ---- sampling warps ----
+    const int sw = warp;  // owns rows kPx sw .. kPx sw + kPx - 1 of a tile, column = lane
+    const int sub = lane & 3;
+    const uint32_t out_sel = sub == 0 ? 0x4210u : (sub == 1 ? 0x5421u : 0x6542u);
+    uint32_t outp = s_out + (kPx * sw) * (kTileW * 3) + (3 * (lane >> 2) + sub) * 4;
+    uint32_t flags = (sub != 3 ? 1u : 0u) | (lane == 0 ? 2u : 0u);
+    asm volatile("" : "+r"(outp), "+r"(flags));
+
+    auto load_entries = [&](int u, uint32_t (&e)[kPx]) {
+        const int grp = u / sp.n_tiles, tile = u - grp * sp.n_tiles;
+        const uint32_t* ent = packed_entries(a.view[grp].packed, sp.n_tiles) + ((size_t)tile * kSamplers + tid) * kPx;
+        if constexpr (kPx == 4) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(ent));
+            e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w;
+        } else if constexpr (kPx == 2) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(ent));
+            e[0] = v.x; e[1] = v.y;
+        } else {
+            e[0] = __ldg(ent);
+        }
+    };
+
+    int n = 0, st = 0;
+    uint32_t ph = 0;
+    int u = blockIdx.x;
+    PackedHdr hn;
+    uint32_t en[kPx];
+    if (u < sp.n_units) {
+        hn = packed_header(a.view[u / sp.n_tiles].packed, (unsigned)(u % sp.n_tiles));
+        load_entries(u, en);
+    }
+    for (; u < sp.n_units; u += stride) {
+        const PackedHdr hdr = hn;
+        uint32_t e[kPx];
+#pragma unroll
+        for (int k = 0; k < kPx; ++k) e[k] = en[k];
+        const int un = u + stride;
+        if (un < sp.n_units) {  // the next tile's header and entries travel while this one is sampled
+            hn = packed_header(a.view[un / sp.n_tiles].packed, (unsigned)(un % sp.n_tiles));
+            load_entries(un, en);
+        }
+        const UnitGeom g = unit_geom<M>(hdr, sp.zero_border, src_cols, src_rows);
+        const int grp = u / sp.n_tiles, tile = u - grp * sp.n_tiles;
+        const int ty = tile / sp.tiles_x, tx = tile - ty * sp.tiles_x;
+        const int x0 = tx * kTileW, y0 = ty * M::kTileH;
+
+        if (!g.fast) {  // per-pixel gather from global memory with full border handling (rare tiles)
+            const ViewArgs& mv = a.view[grp];
+#pragma unroll 1
+            for (int k = 0; k < kPx; ++k) {
+                const int i = x0 + lane, j = y0 + kPx * sw + k;
+                if (i >= a.W || j >= a.H) continue;
+                int qx, qy;
+                if (hdr.flags & 1) {
+                    qx = ((hdr.mnx + (int)(e[k] & 255u)) << M::kShift) | (int)((e[k] >> 16) & 31u);
+                    qy = ((hdr.mny + (int)((e[k] >> 8) & 255u)) << M::kShift) | (int)((e[k] >> 21) & 31u);
+                } else {
+                    qx = M::quant(__ldg(mv.xmap + (long long)j * mv.map_pitch + i));
+                    qy = M::quant(__ldg(mv.ymap + (long long)j * mv.map_pitch + i));
+                }
+                for (int f = 0; f < a.n_frames; ++f) {
+                    uint8_t* drow = a.dst + (long long)f * a.dst_frame_stride + (long long)j * a.dst_pitch;
+                    for (int v = grp; v < grp + nv; ++v) {
+                        const ViewArgs& vw = a.view[v];
+                        Src s{vw.src + (long long)f * vw.frame_stride, vw.rows, vw.cols, vw.pitch};
+                        int px[3];
+                        if (M::kInterp == VR180_INTER_NEAREST)
+                            fetch_tap<3>(s, sat16(qx), sat16(qy), a.border_mode, a.bv, px);
+                        else if (M::kInterp == VR180_INTER_LINEAR)
+                            sample_linear<3>(s, qx, qy, a.border_mode, a.bv, px);
+                        else if (M::kInterp == VR180_INTER_CUBIC)
+                            sample_tab<3, 4>(s, qx, qy, sp.tab, a.border_mode, a.bv, px);
+                        else
+                            sample_tab<3, 8>(s, qx, qy, sp.tab, a.border_mode, a.bv, px);
+                        uint8_t* o = drow + (long long)(vw.dst_x_offset + i) * 3;
+                        o[0] = (uint8_t)px[0];
+                        o[1] = (uint8_t)px[1];
+                        o[2] = (uint8_t)px[2];
+                    }
+                }
+            }
+            continue;
+        }
+
+        // ---- sampling constants of this thread's pixels ----
+        typename M::Pixel pc[kPx];
+        const int org = 3 * (hdr.mnx - M::kLo) - g.bx0;  // byte column of the tile's first tap column inside the rectangle
+#pragma unroll
+        for (int k = 0; k < kPx; ++k) {
+            const int dx = (int)(e[k] & 255u), dy = (int)((e[k] >> 8) & 255u);  // iy - kLo - ry0 == dy
+            M::set_offset(pc[k], dy * g.pitch + 3 * dx + org, true);
+            M::weights(pc[k], (int)((e[k] >> 16) & 31u), (int)((e[k] >> 21) & 31u), sp.tab);
+        }
+        if constexpr (M::kWeightSmem != 0) {  // Lanczos4: the pixel's 64 weights, private copy in shared memory
+            uint8_t* slot = smem + SLay<M>::kOffW + tid * 16;
+#pragma unroll
+            for (int ky = 0; ky < 8; ++ky)
+                *reinterpret_cast<uint4*>(slot + ky * (kSamplers * 16)) = __ldg(reinterpret_cast<const uint4*>(pc[0].w) + ky);
+            pc[0].ws = smem_u32(slot);
+        }
+
+        const int n_items = a.n_frames * nv;
+#pragma unroll 1
+        for (int it = 0; it < n_items; ++it) {
+            mbar_wait(s_full + st * 8, ph);
+            const uint32_t buf = s_stage + st * kSlotBytes;
+            uint32_t word[kPx];
+#pragma unroll
+            for (int k = 0; k < kPx; ++k) {
+                const uint32_t r = M::sample(buf, pc[k], (uint32_t)g.pitch);
+                word[k] = __byte_perm(r, __shfl_down_sync(0xffffffffu, r, 1), out_sel);
+            }
+            const int o = n & (kOB - 1);
+            if (n >= kOB) mbar_wait(s_oempty + o * 8, (uint32_t)(n / kOB + 1) & 1u);  // store n - kOB has read out[o]
+            if (flags & 1u) {
+                const uint32_t ob = outp + o * kOutTileBytes;
+#pragma unroll
+                for (int k = 0; k < kPx; ++k) sts32(ob + k * (kTileW * 3), word[k]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (flags & 2u) mbar_arrive(s_ofull + o * 8);  // this warp's rows of the item are in out[o]; it has left the slot
+            ++n;
+            if (++st == kSlots) { st = 0; ph ^= 1u; }
+        }
+    }
+}
+
+template <class M>
+static int launch_stream_mode(const RemapArgs& a, const short* tab, cudaStream_t st) {
+    const int n_groups = a.share_map ? 1 : a.n_views;
+    const TmaMaps* tm = tma_maps_for(a, M::kInterp, M::kRowsMin, M::kTileH, 1);
+    if (!tm) return VR180_ERR_UNSUPPORTED;
+    static std::atomic<int> attr_done[64];
+    int dev = 0;
+    VR180_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_done[dev].load(std::memory_order_acquire)) {
+        VR180_CUDA(cudaFuncSetAttribute(k_warp_stream<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLay<M>::kSmemBytes));
+        attr_done[dev].store(1, std::memory_order_release);
+    }
+    static std::atomic<int> sm_count[64];
+    int sms = dev < 64 ? sm_count[dev].load(std::memory_order_acquire) : 0;
+    if (!sms) {
+        VR180_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (dev < 64) sm_count[dev].store(sms, std::memory_order_release);
+    }
+    StreamParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.tiles_x = (a.W + kTileW - 1) / kTileW;
+    const long long tiles = (long long)sp.tiles_x * ((a.H + M::kTileH - 1) / M::kTileH);
+    if (tiles * n_groups > 0x7fffffffLL) return VR180_ERR_UNSUPPORTED;
+    sp.n_tiles = (int)tiles;
+    sp.n_units = (int)(tiles * n_groups);
+    sp.zero_border = (a.border_mode == VR180_BORDER_CONSTANT && !(a.bv[0] | a.bv[1] | a.bv[2])) ? 1 : 0;
+    sp.tab = tab;
+    const int forced = g_debug_stream_grid.load(std::memory_order_relaxed);  // vr180_debug_set(3, n): tests
+    int grid = forced > 0 ? forced : sms * 4;
+    if (grid > sp.n_units) grid = sp.n_units;
+    k_warp_stream<M><<<grid, kThreads, SLay<M>::kSmemBytes, st>>>(a, sp, *tm);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    VR180_CUDA(cudaGetLastError());
+    return VR180_OK;
+}
+
+}  // namespace tiled
+
+// Eligibility is decided by the caller (launch_remap_tiled: 3 channels, aligned buffers, every map group with a packed LUT
+// of this interpolation, no per-frame radius).
+int launch_remap_stream(const RemapArgs& a, int interp, const short* weight_tab, cudaStream_t st) {
+    using namespace tiled;
+    if (interp == VR180_INTER_NEAREST) return launch_stream_mode<Nearest>(a, nullptr, st);
+    if (interp == VR180_INTER_LINEAR) return launch_stream_mode<LinearP>(a, nullptr, st);
+    if (interp == VR180_INTER_CUBIC) return launch_stream_mode<Cubic>(a, weight_tab, st);
+    if (interp == VR180_INTER_LANCZOS4) return launch_stream_mode<Lanczos4>(a, weight_tab, st);
+    return VR180_ERR_UNSUPPORTED;
+}
+
+}  // namespace vr180
