@@ -25,18 +25,24 @@
 namespace vr180 {
 namespace tiled {
 
-constexpr int kSlots = 3;  // stage ring: slots of Lay<M>::kStageArea / 3 bytes (13.5 KB; a bilinear 8K tile needs <= 10.5 KB)
+constexpr int kSlots = 3;       // stage ring: slots of Lay<M>::kStageArea / 3 bytes (13.5 KB; a bilinear 8K tile needs <= 10.5 KB)
+constexpr int kStreamCtas = 3;  // CTAs per SM (72 registers: the constants of the next tile are prefetched beside the current one's)
 
 template <class M>
 struct SLay {
-    static constexpr int kSlotBytes = (Lay<M>::kStageArea / kSlots) & ~127;
+    static constexpr int kSlotBytes = kStreamSlotBytes<M>;
+    static_assert(kSlots == 3, "kStreamSlotBytes (tiled.cuh) is a third of the staging area");
     static constexpr int kOutTileBytes = M::kTileH * kTileW * 3;
     static constexpr int kOB = kOutBufs;  // out buffers of one tile each
     static constexpr int kOffOut = kSlots * kSlotBytes;
     static constexpr int kOffBar = kOffOut + kOB * kOutTileBytes;  // full[kSlots], ofull[kOB], oempty[kOB]
     static constexpr int kOffQ = (kOffBar + (kSlots + 2 * kOB) * 8 + 15) & ~15;  // int4 per slot: store coordinates of the item in it
     static constexpr int kOffW = (kOffQ + kSlots * 16 + 15) & ~15;
-    static constexpr int kSmemBytes = kOffW + M::kWeightSmem;
+    // bilinear: the packed weight pairs {W01, W23} of all 32 x 32 sub-pixel positions, built once per CTA -- a tile's
+    // pixels then fetch their weights with one LDS.64 instead of computing four products and two packs each
+    static constexpr int kWeightTab = M::kInterp == VR180_INTER_LINEAR ? 1024 * 8 : 0;
+    static constexpr int kOffTab = kOffW + M::kWeightSmem;
+    static constexpr int kSmemBytes = kOffTab + kWeightTab;
 };
 
 struct StreamParams {
@@ -45,29 +51,31 @@ struct StreamParams {
     const short* tab;
 };
 
-// Source rectangle of a packed tile from its header alone (both the producer and the sampling warps evaluate it).
+// Source rectangle of a packed tile from its header alone (both the producer and the sampling warps evaluate it): the
+// box sizes were chosen by k_pack_tiles, only the origin and the border test are left.
 struct UnitGeom {
-    int fast, bx0, ry0, pitch, rsel, rect_bytes;
+    int fast, bx0, ry0, pitch, rsel, rect_bytes, org;
 };
 template <class M>
 __device__ __forceinline__ UnitGeom unit_geom(const PackedHdr& h, int zero_border, int src_cols, int src_rows) {
     UnitGeom g;
-    const int mnx = h.mnx, mxx = h.mxx, mny = h.mny, mxy = h.mxy;
-    g.bx0 = (3 * (mnx - M::kLo)) & ~15;
-    const int bx1 = (3 * (mxx + M::kHi + 1) + 15) & ~15;
-    g.ry0 = mny - M::kLo;
-    const int wbytes = bx1 - g.bx0, nrows = mxy + M::kHi + 1 - g.ry0;
-    g.pitch = max(wbytes, kPitchMin);
-    g.rsel = nrows <= M::kRowsMin ? 0 : (nrows - M::kRowsMin + kRowsStep - 1) / kRowsStep;
+    const int c0 = 3 * ((int)h.mnx - M::kLo);  // byte column of the tile's first tap column
+    g.bx0 = c0 & ~15;
+    g.org = c0 & 15;
+    g.ry0 = (int)h.mny - M::kLo;
+    g.pitch = kPitchMin + kPitchStep * ((h.flags >> 8) & 15);
+    g.rsel = (h.flags >> 12) & 15;
     g.rect_bytes = (M::kRowsMin + g.rsel * kRowsStep) * g.pitch;
-    const bool inside = mnx - M::kLo >= 0 && mxx + M::kHi <= src_cols - 1 && mny - M::kLo >= 0 && mxy + M::kHi <= src_rows - 1;
-    g.fast = (h.flags & 1) && wbytes <= kPitchMax && g.rsel < kRowSizes && g.rect_bytes <= SLay<M>::kSlotBytes &&
-             (zero_border || inside);
+    constexpr int kAll = kHdrPackable | kHdrStageable | kHdrFitsSlot;
+    g.fast = (h.flags & kAll) == kAll;
+    if (!zero_border)  // any other border needs real taps where the footprint leaves the source: per-pixel path
+        g.fast = g.fast && (int)h.mnx - M::kLo >= 0 && (int)h.mxx + M::kHi <= src_cols - 1 && (int)h.mny - M::kLo >= 0 &&
+                 (int)h.mxy + M::kHi <= src_rows - 1;
     return g;
 }
 
 template <class M>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, kStreamCtas)
 k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ StreamParams sp,
               const __grid_constant__ TmaMaps tm) {
     constexpr int kPx = M::kPx;
@@ -81,6 +89,14 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
         const bool by_warps = tid >= kSlots && tid < kSlots + kOB;  // ofull: one arrive per sampling warp
         mbar_init(s_full + tid * 8, by_warps ? kSamplers / 32 : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if constexpr (SLay<M>::kWeightTab != 0) {
+        uint2* const wt = reinterpret_cast<uint2*>(smem + SLay<M>::kOffTab);
+        for (int i = tid; i < 1024; i += kThreads) {
+            typename M::Pixel p;
+            M::weights(p, i & 31, i >> 5, nullptr);
+            wt[i] = make_uint2(p.W01, p.W23);
+        }
     }
     __syncthreads();
     const int nv = a.share_map ? a.n_views : 1;
@@ -101,16 +117,17 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
             ++n_store;
             if (++s_slot == kSlots) s_slot = 0;
         };
-        int u = blockIdx.x;
-        PackedHdr hn;
-        if (u < sp.n_units) hn = packed_header(a.view[u / sp.n_tiles].packed, (unsigned)(u % sp.n_tiles));
-        for (; u < sp.n_units; u += stride) {
+        int grp_n = 0, tile_n = blockIdx.x;  // unit = (map group, tile); blockIdx.x < n_units
+        while (tile_n >= sp.n_tiles) { tile_n -= sp.n_tiles; ++grp_n; }
+        PackedHdr hn = packed_header(a.view[grp_n].packed, (unsigned)tile_n);
+        for (int u = blockIdx.x; u < sp.n_units; u += stride) {
             const PackedHdr hdr = hn;
-            const int un = u + stride;
-            if (un < sp.n_units) hn = packed_header(a.view[un / sp.n_tiles].packed, (unsigned)(un % sp.n_tiles));
+            const int grp = grp_n, tile = tile_n;
+            tile_n += stride;
+            while (tile_n >= sp.n_tiles) { tile_n -= sp.n_tiles; ++grp_n; }
+            if (u + stride < sp.n_units) hn = packed_header(a.view[grp_n].packed, (unsigned)tile_n);
             const UnitGeom g = unit_geom<M>(hdr, sp.zero_border, src_cols, src_rows);
             if (!g.fast) continue;
-            const int grp = u / sp.n_tiles, tile = u - grp * sp.n_tiles;
             const int ty = tile / sp.tiles_x, tx = tile - ty * sp.tiles_x;
             const CUtensorMap* const map0 = &tm.src[grp][(g.pitch - kPitchMin) / kPitchStep][g.rsel];
             for (int f = 0; f < a.n_frames; ++f) {
@@ -138,8 +155,7 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
     uint32_t flags = (sub != 3 ? 1u : 0u) | (lane == 0 ? 2u : 0u);
     asm volatile("" : "+r"(outp), "+r"(flags));
 
-    auto load_entries = [&](int u, uint32_t (&e)[kPx]) {
-        const int grp = u / sp.n_tiles, tile = u - grp * sp.n_tiles;
+    auto load_entries = [&](int grp, int tile, uint32_t (&e)[kPx]) {
         const uint32_t* ent = packed_entries(a.view[grp].packed, sp.n_tiles) + ((size_t)tile * kSamplers + tid) * kPx;
         if constexpr (kPx == 4) {
             const uint4 v = __ldg(reinterpret_cast<const uint4*>(ent));
@@ -154,36 +170,35 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
 
     int n = 0, st = 0;
     uint32_t ph = 0;
-    int u = blockIdx.x;
-    PackedHdr hn;
+    int grp_n = 0, tile_n = blockIdx.x;  // unit = (map group, tile); blockIdx.x < n_units
+    while (tile_n >= sp.n_tiles) { tile_n -= sp.n_tiles; ++grp_n; }
+    PackedHdr hn = packed_header(a.view[grp_n].packed, (unsigned)tile_n);
     uint32_t en[kPx];
-    if (u < sp.n_units) {
-        hn = packed_header(a.view[u / sp.n_tiles].packed, (unsigned)(u % sp.n_tiles));
-        load_entries(u, en);
-    }
-    for (; u < sp.n_units; u += stride) {
+    load_entries(grp_n, tile_n, en);
+    for (int u = blockIdx.x; u < sp.n_units; u += stride) {
         const PackedHdr hdr = hn;
         uint32_t e[kPx];
 #pragma unroll
         for (int k = 0; k < kPx; ++k) e[k] = en[k];
-        const int un = u + stride;
-        if (un < sp.n_units) {  // the next tile's header and entries travel while this one is sampled
-            hn = packed_header(a.view[un / sp.n_tiles].packed, (unsigned)(un % sp.n_tiles));
-            load_entries(un, en);
+        const int grp = grp_n, tile = tile_n;
+        tile_n += stride;
+        while (tile_n >= sp.n_tiles) { tile_n -= sp.n_tiles; ++grp_n; }
+        if (u + stride < sp.n_units) {  // the next tile's header and entries travel while this one is sampled
+            hn = packed_header(a.view[grp_n].packed, (unsigned)tile_n);
+            load_entries(grp_n, tile_n, en);
         }
         const UnitGeom g = unit_geom<M>(hdr, sp.zero_border, src_cols, src_rows);
-        const int grp = u / sp.n_tiles, tile = u - grp * sp.n_tiles;
-        const int ty = tile / sp.tiles_x, tx = tile - ty * sp.tiles_x;
-        const int x0 = tx * kTileW, y0 = ty * M::kTileH;
 
         if (!g.fast) {  // per-pixel gather from global memory with full border handling (rare tiles)
             const ViewArgs& mv = a.view[grp];
+            const int ty = tile / sp.tiles_x, tx = tile - ty * sp.tiles_x;
+            const int x0 = tx * kTileW, y0 = ty * M::kTileH;
 #pragma unroll 1
             for (int k = 0; k < kPx; ++k) {
                 const int i = x0 + lane, j = y0 + kPx * sw + k;
                 if (i >= a.W || j >= a.H) continue;
                 int qx, qy;
-                if (hdr.flags & 1) {
+                if (hdr.flags & kHdrPackable) {
                     qx = ((hdr.mnx + (int)(e[k] & 255u)) << M::kShift) | (int)((e[k] >> 16) & 31u);
                     qy = ((hdr.mny + (int)((e[k] >> 8) & 255u)) << M::kShift) | (int)((e[k] >> 21) & 31u);
                 } else {
@@ -216,12 +231,17 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
 
         // ---- sampling constants of this thread's pixels ----
         typename M::Pixel pc[kPx];
-        const int org = 3 * (hdr.mnx - M::kLo) - g.bx0;  // byte column of the tile's first tap column inside the rectangle
 #pragma unroll
         for (int k = 0; k < kPx; ++k) {
             const int dx = (int)(e[k] & 255u), dy = (int)((e[k] >> 8) & 255u);  // iy - kLo - ry0 == dy
-            M::set_offset(pc[k], dy * g.pitch + 3 * dx + org, true);
-            M::weights(pc[k], (int)((e[k] >> 16) & 31u), (int)((e[k] >> 21) & 31u), sp.tab);
+            M::set_offset(pc[k], dy * g.pitch + 3 * dx + g.org, true);
+            if constexpr (SLay<M>::kWeightTab != 0) {
+                asm("ld.shared.v2.u32 {%0, %1}, [%2];"
+                    : "=r"(pc[k].W01), "=r"(pc[k].W23)
+                    : "r"(s_stage + SLay<M>::kOffTab + ((e[k] >> 13) & (1023u << 3))));
+            } else {
+                M::weights(pc[k], (int)((e[k] >> 16) & 31u), (int)((e[k] >> 21) & 31u), sp.tab);
+            }
         }
         if constexpr (M::kWeightSmem != 0) {  // Lanczos4: the pixel's 64 weights, private copy in shared memory
             uint8_t* slot = smem + SLay<M>::kOffW + tid * 16;
@@ -286,7 +306,7 @@ static int launch_stream_mode(const RemapArgs& a, const short* tab, cudaStream_t
     sp.zero_border = (a.border_mode == VR180_BORDER_CONSTANT && !(a.bv[0] | a.bv[1] | a.bv[2])) ? 1 : 0;
     sp.tab = tab;
     const int forced = g_debug_stream_grid.load(std::memory_order_relaxed);  // vr180_debug_set(3, n): tests
-    int grid = forced > 0 ? forced : sms * 4;
+    int grid = forced > 0 ? forced : sms * kStreamCtas;
     if (grid > sp.n_units) grid = sp.n_units;
     k_warp_stream<M><<<grid, kThreads, SLay<M>::kSmemBytes, st>>>(a, sp, *tm);
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -723,11 +723,56 @@ __global__ void __launch_bounds__(kSamplers) k_pack_tiles(const float* __restric
     }
     const bool ok = full_tile && mnx > -32768 && mny > -32768 && mxx < 32767 && mxy < 32767 && mxx - mnx <= 255 &&
                     mxy - mny <= 255;
+    // Geometry of the tile's source rectangle for the tile-streaming kernel (stream.cu), which has no time to derive it
+    // per launch: box rows, and the row pitch (= TMA box width) with the fewest shared-memory wavefronts among the
+    // kPitchCands tightest -- the bank conflicts of the tile's own tap addresses (every warp counts, with match.any, the
+    // distinct words per bank of the first tap load of its first row) + the TMA write of the box, as k_warp_tiled does.
+    __shared__ int s_cost[kPitchCands];
+    if (tid < kPitchCands) s_cost[tid] = 0;
+    __syncthreads();
+    const int bx0 = (3 * (mnx - M::kLo)) & ~15, bx1 = (3 * (mxx + M::kHi + 1) + 15) & ~15, ry0 = mny - M::kLo;
+    const int wbytes = bx1 - bx0, nrows = mxy + M::kHi + 1 - ry0;
+    const int rsel = nrows <= M::kRowsMin ? 0 : (nrows - M::kRowsMin + kRowsStep - 1) / kRowsStep;
+    const int box_rows = M::kRowsMin + rsel * kRowsStep;
+    const int pitch0 = max(wbytes, kPitchMin);
+    const bool stageable = ok && wbytes <= kPitchMax && rsel < kRowSizes;
+    int widx = 0;
+    if (stageable) {  // CTA-uniform
+        const int row = (sy[0] >> M::kShift) - M::kLo - ry0, col = 3 * ((sx[0] >> M::kShift) - M::kLo) - bx0;
+        int cost = 0;
+#pragma unroll
+        for (int e = 0; e < kPitchCands; ++e) {
+            const int w = (row * (pitch0 + kPitchStep * e) + col) >> 2;
+            const unsigned same = __match_any_sync(0xffffffffu, w);
+            const bool leader = (__ffs(same) - 1) == lane;  // one lane per distinct word
+            const unsigned lm = __ballot_sync(0xffffffffu, leader);
+            int deg = 0;
+            if (leader) deg = __popc(__match_any_sync(lm, w & 31));
+            deg = __reduce_max_sync(0xffffffffu, deg);
+            if (lane == e) cost = deg;
+        }
+        constexpr int kStepsPerWarp = M::kTileH * kTileW / kSamplers;
+        constexpr int kLoadsPerTile = kStepsPerWarp * (M::kInterp == VR180_INTER_NEAREST ? 2 : M::kInterp == VR180_INTER_LINEAR ? 6
+                                                       : M::kInterp == VR180_INTER_CUBIC ? 16 : 56);
+        if (lane < kPitchCands) atomicAdd(&s_cost[lane], cost * kLoadsPerTile);
+    }
+    __syncthreads();
+    if (stageable) {
+        int best_cost = INT_MAX;
+#pragma unroll
+        for (int e = 0; e < kPitchCands; ++e) {
+            const int pe = pitch0 + kPitchStep * e;
+            const int c = s_cost[e] + box_rows * pe / 64;
+            if (pe <= kPitchMax && (e == 0 || box_rows * pe <= kStreamSlotBytes<M>) && c < best_cost) { best_cost = c; widx = (pe - kPitchMin) / kPitchStep; }
+        }
+    }
+    const int pitch = kPitchMin + kPitchStep * widx;
     if (tid == 0) {
         int4 h;
         h.x = (mnx & 0xffff) | (mxx << 16);
         h.y = (mny & 0xffff) | (mxy << 16);
-        h.z = ok ? 1 : 0;
+        h.z = (ok ? kHdrPackable : 0) | (stageable ? kHdrStageable : 0) |
+              (stageable && box_rows * pitch <= kStreamSlotBytes<M> ? kHdrFitsSlot : 0) | (widx << 8) | (rsel << 12);
         h.w = 0;
         reinterpret_cast<int4*>(packed)[blockIdx.x] = h;
     }

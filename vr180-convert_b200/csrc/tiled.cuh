@@ -47,6 +47,10 @@ struct Lay {
     static constexpr int kSmemBytes = kOffW + M::kWeightSmem;
 };
 
+// stage slot of the tile-streaming kernel (stream.cu): a ring of 3 fixed-size slots in the mode's staging area
+template <class M>
+constexpr int kStreamSlotBytes = (M::kStageArea / 3) & ~127;
+
 // The standard chain shape, lowered once on the host (see match_std_chain):
 //   Normalize, EquirectangularEncoder, [Euclidean3DRotator], [PolynomialScaler], FisheyeDecoder("equidistant"),
 //   Denormalize
@@ -80,9 +84,13 @@ struct alignas(64) TmaMaps {
 // entry  = (ix - mnx) | (iy - mny) << 8 | ax << 16 | ay << 21     (ax = ay = 0 for INTER_NEAREST)
 struct PackedHdr {
     short mnx, mxx, mny, mxy;  // integer source coordinates of the tile: min / max of ix and iy
-    int flags;                 // bit 0: packable (full tile, finite unsaturated coordinates, extents <= 255)
+    int flags;                 // kHdr* bits | box width index << 8 | box row index << 12 (see k_pack_tiles)
     int pad;
 };
+constexpr int kHdrPackable = 1;   // full tile, finite unsaturated coordinates, extents <= 255: the entries are valid
+constexpr int kHdrStageable = 2;  // the source rectangle fits a TMA box of this mode (width <= kPitchMax, rows <= the largest box)
+constexpr int kHdrFitsSlot = 4;   // ... and one stage slot of the tile-streaming kernel
+// bits 8-11: (row pitch - kPitchMin) / kPitchStep chosen for the tile; bits 12-15: box rows = kRowsMin + kRowsStep * r
 static_assert(sizeof(PackedHdr) == 16, "PackedHdr is one 128-bit load");
 __host__ __device__ inline size_t packed_entries_offset(long long n_tiles) { return ((size_t)n_tiles * 16 + 255) & ~(size_t)255; }
 __device__ __forceinline__ PackedHdr packed_header(const void* packed, unsigned tile) {
@@ -256,9 +264,11 @@ struct LinearP {
         uint32_t W01, W23;
     };
     __device__ static __forceinline__ void set_offset(Pixel& p, int off, bool valid) {
+        // selA = s | (s + 3) << 4 = 0x30 + 0x11 s;  selT = (s + 1) | (s + 4) << 4 | (s + 2) << 8 | (s + 5) << 12 = 0x5241 +
+        // 0x1111 s for s < 3 and 0x0574 = (0x5241 + 0x3333) & 0x7fff for s == 3
         const uint32_t s = (uint32_t)off & 3u;
-        p.osel = ((valid ? ((uint32_t)off & ~3u) : 0u) << 16) | s | ((s + 3u) << 4);
-        p.selT = s == 3u ? 0x0574u : ((s + 1u) | ((s + 4u) << 4) | ((s + 2u) << 8) | ((s + 5u) << 12));
+        p.osel = ((valid ? ((uint32_t)off & ~3u) : 0u) << 16) | (0x30u + 0x11u * s);
+        p.selT = (0x5241u + 0x1111u * s) & 0x7fffu;
     }
     __device__ static __forceinline__ void weights(Pixel& p, int ax, int ay, const short* t) {
         Linear::Pixel q;
