@@ -142,3 +142,25 @@ def test_stream_long_run_through_one_cta(hooks):
     m = chain_np.get_map(_ops(QL), radius=170.0, size_input=(hin, win), size_output=(wout, hout))
     want = np.concatenate([cv2.remap(ln[0], m[0], m[1], interpolation=1), cv2.remap(rn[0], m[0], m[1], interpolation=1)], axis=1)
     assert np.array_equal(got[0], want), int((got[0] != want).sum())
+
+
+def test_stream_more_unstaged_tiles_than_the_list_holds(hooks):
+    """BORDER_REPLICATE with a radius far beyond the source: most of the 640 tiles leave the source and are left to the
+    per-pixel gather.  One CTA notes at most 128 of them before it stops streaming, gathers them and resumes."""
+    import torch
+
+    hin, win, wout, hout = 300, 360, 1024, 640
+    rng = np.random.default_rng(10)
+    ln = rng.integers(0, 256, (1, hin, win, 3), dtype=np.uint8)
+    rn = rng.integers(0, 256, (1, hin, win, 3), dtype=np.uint8)
+    wp = V.SbsWarper(_chain(QL), size_input=(hin, win), size_output=(wout, hout), interpolation=1, radius=420.0,
+                     map_source="lut_packed", boarder_mode=cv2.BORDER_REPLICATE)
+    hooks(1, 2)
+    got = wp(torch.from_numpy(ln).cuda(), torch.from_numpy(rn).cuda()).cpu().numpy()
+    m = chain_np.get_map(_ops(QL), radius=420.0, size_input=(hin, win), size_output=(wout, hout))
+    ix, iy = np.floor(m[0]), np.floor(m[1])
+    outside = ((ix < 0) | (ix + 1 > win - 1) | (iy < 0) | (iy + 1 > hin - 1)).reshape(hout // 32, 32, wout // 32, 32).any(axis=(1, 3))
+    assert 128 < outside.sum() < outside.size, outside.sum()  # the list overflows, and staged tiles remain
+    want = np.concatenate([cv2.remap(ln[0], m[0], m[1], interpolation=1, borderMode=cv2.BORDER_REPLICATE),
+                           cv2.remap(rn[0], m[0], m[1], interpolation=1, borderMode=cv2.BORDER_REPLICATE)], axis=1)
+    assert np.array_equal(got[0], want), int((got[0] != want).sum())

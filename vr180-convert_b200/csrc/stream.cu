@@ -26,14 +26,15 @@ namespace vr180 {
 namespace tiled {
 
 constexpr int kSlots = 3;       // stage ring: slots of Lay<M>::kStageArea / 3 bytes (13.5 KB; a bilinear 8K tile needs <= 10.5 KB)
+constexpr int kSlowCap = 128;   // non-staged tiles a CTA notes before it stops streaming to gather them
 constexpr int kStreamCtas = 3;  // CTAs per SM (72 registers: the constants of the next tile are prefetched beside the current one's)
 
-template <class M>
+template <class M, int CTAS = kStreamCtas>
 struct SLay {
     static constexpr int kSlotBytes = kStreamSlotBytes<M>;
     static_assert(kSlots == 3, "kStreamSlotBytes (tiled.cuh) is a third of the staging area");
     static constexpr int kOutTileBytes = M::kTileH * kTileW * 3;
-    static constexpr int kOB = kOutBufs;  // out buffers of one tile each
+    static constexpr int kOB = CTAS >= 4 ? 2 : kOutBufs;  // out buffers of one tile each
     static constexpr int kOffOut = kSlots * kSlotBytes;
     static constexpr int kOffBar = kOffOut + kOB * kOutTileBytes;  // full[kSlots], ofull[kOB], oempty[kOB]
     static constexpr int kOffQ = (kOffBar + (kSlots + 2 * kOB) * 8 + 15) & ~15;  // int4 per slot: store coordinates of the item in it
@@ -42,7 +43,8 @@ struct SLay {
     // pixels then fetch their weights with one LDS.64 instead of computing four products and two packs each
     static constexpr int kWeightTab = M::kInterp == VR180_INTER_LINEAR ? 1024 * 8 : 0;
     static constexpr int kOffTab = kOffW + M::kWeightSmem;
-    static constexpr int kSmemBytes = kOffTab + kWeightTab;
+    static constexpr int kOffSlow = kOffTab + kWeightTab;  // int2 (map group, tile) of the tiles left to the per-pixel gather
+    static constexpr int kSmemBytes = kOffSlow + kSlowCap * 8;
 };
 
 struct StreamParams {
@@ -53,12 +55,16 @@ struct StreamParams {
 
 // Source rectangle of a packed tile from its header alone (both the producer and the sampling warps evaluate it): the
 // box sizes were chosen by k_pack_tiles, only the origin and the border test are left.
+__device__ __forceinline__ int4 raw_header(const void* packed, int tile) {
+    return __ldg(reinterpret_cast<const int4*>(packed) + tile);
+}
 struct UnitGeom {
     int fast, bx0, ry0, pitch, rsel, rect_bytes, org;
 };
 template <class M>
-__device__ __forceinline__ UnitGeom unit_geom(const PackedHdr& h, int zero_border, int src_cols, int src_rows) {
+__device__ __forceinline__ UnitGeom unit_geom(const int4& raw, int zero_border, int src_cols, int src_rows) {
     UnitGeom g;
+    struct { int mnx, mxx, mny, mxy, flags; } h = {(short)(raw.x & 0xffff), raw.x >> 16, (short)(raw.y & 0xffff), raw.y >> 16, raw.z};
     const int c0 = 3 * ((int)h.mnx - M::kLo);  // byte column of the tile's first tap column
     g.bx0 = c0 & ~15;
     g.org = c0 & 15;
@@ -74,24 +80,74 @@ __device__ __forceinline__ UnitGeom unit_geom(const PackedHdr& h, int zero_borde
     return g;
 }
 
+// Tiles that are not staged: per-pixel gather from global memory with full border handling (rare: partial edge tiles,
+// NaN / huge coordinates, footprints beyond a stage slot, the source edge under a non-zero border).  The pixel loop is
+// unrolled: an indexed access to the entries would put them in local memory for the streaming loop too.
+template <int N>
+struct Entries {
+    uint32_t e[N];
+};
 template <class M>
-__global__ void __launch_bounds__(kThreads, kStreamCtas)
+__device__ __forceinline__ void gather_tile(const RemapArgs& a, const StreamParams& sp, int grp, int tile, int nv, bool packed,
+                                         int mnx, int mny, Entries<M::kPx> ev) {
+    constexpr int kPx = M::kPx;
+    const int tid = threadIdx.x, lane = tid & 31, sw = tid >> 5;
+    const ViewArgs& mv = a.view[grp];
+    const int ty = tile / sp.tiles_x, tx = tile - ty * sp.tiles_x;
+    const int x0 = tx * kTileW, y0 = ty * M::kTileH;
+#pragma unroll
+    for (int k = 0; k < kPx; ++k) {
+        const int i = x0 + lane, j = y0 + kPx * sw + k;
+        if (i >= a.W || j >= a.H) continue;
+        int qx, qy;
+        if (packed) {
+            qx = ((mnx + (int)(ev.e[k] & 255u)) << M::kShift) | (int)((ev.e[k] >> 16) & 31u);
+            qy = ((mny + (int)((ev.e[k] >> 8) & 255u)) << M::kShift) | (int)((ev.e[k] >> 21) & 31u);
+        } else {
+            qx = M::quant(__ldg(mv.xmap + (long long)j * mv.map_pitch + i));
+            qy = M::quant(__ldg(mv.ymap + (long long)j * mv.map_pitch + i));
+        }
+        for (int f = 0; f < a.n_frames; ++f) {
+            uint8_t* drow = a.dst + (long long)f * a.dst_frame_stride + (long long)j * a.dst_pitch;
+            for (int v = grp; v < grp + nv; ++v) {
+                const ViewArgs& vw = a.view[v];
+                Src s{vw.src + (long long)f * vw.frame_stride, vw.rows, vw.cols, vw.pitch};
+                int px[3];
+                if (M::kInterp == VR180_INTER_NEAREST)
+                    fetch_tap<3>(s, sat16(qx), sat16(qy), a.border_mode, a.bv, px);
+                else if (M::kInterp == VR180_INTER_LINEAR)
+                    sample_linear<3>(s, qx, qy, a.border_mode, a.bv, px);
+                else if (M::kInterp == VR180_INTER_CUBIC)
+                    sample_tab<3, 4>(s, qx, qy, sp.tab, a.border_mode, a.bv, px);
+                else
+                    sample_tab<3, 8>(s, qx, qy, sp.tab, a.border_mode, a.bv, px);
+                uint8_t* o = drow + (long long)(vw.dst_x_offset + i) * 3;
+                o[0] = (uint8_t)px[0];
+                o[1] = (uint8_t)px[1];
+                o[2] = (uint8_t)px[2];
+            }
+        }
+    }
+}
+
+template <class M, int CTAS>
+__global__ void __launch_bounds__(kThreads, CTAS)
 k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ StreamParams sp,
               const __grid_constant__ TmaMaps tm) {
     constexpr int kPx = M::kPx;
-    constexpr int kOB = SLay<M>::kOB, kOutTileBytes = SLay<M>::kOutTileBytes, kSlotBytes = SLay<M>::kSlotBytes;
+    constexpr int kOB = SLay<M, CTAS>::kOB, kOutTileBytes = SLay<M, CTAS>::kOutTileBytes, kSlotBytes = SLay<M, CTAS>::kSlotBytes;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t s_stage = smem_u32(smem), s_full = s_stage + SLay<M>::kOffBar;
-    const uint32_t s_ofull = s_full + kSlots * 8, s_oempty = s_ofull + kOB * 8, s_out = s_stage + SLay<M>::kOffOut;
-    int4* const s_q = reinterpret_cast<int4*>(smem + SLay<M>::kOffQ);
+    const uint32_t s_stage = smem_u32(smem), s_full = s_stage + SLay<M, CTAS>::kOffBar;
+    const uint32_t s_ofull = s_full + kSlots * 8, s_oempty = s_ofull + kOB * 8, s_out = s_stage + SLay<M, CTAS>::kOffOut;
+    int4* const s_q = reinterpret_cast<int4*>(smem + SLay<M, CTAS>::kOffQ);
     if (tid < kSlots + 2 * kOB) {
         const bool by_warps = tid >= kSlots && tid < kSlots + kOB;  // ofull: one arrive per sampling warp
         mbar_init(s_full + tid * 8, by_warps ? kSamplers / 32 : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if constexpr (SLay<M>::kWeightTab != 0) {
-        uint2* const wt = reinterpret_cast<uint2*>(smem + SLay<M>::kOffTab);
+    if constexpr (SLay<M, CTAS>::kWeightTab != 0) {
+        uint2* const wt = reinterpret_cast<uint2*>(smem + SLay<M, CTAS>::kOffTab);
         for (int i = tid; i < 1024; i += kThreads) {
             typename M::Pixel p;
             M::weights(p, i & 31, i >> 5, nullptr);
@@ -119,13 +175,13 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
         };
         int grp_n = 0, tile_n = blockIdx.x;  // unit = (map group, tile); blockIdx.x < n_units
         while (tile_n >= sp.n_tiles) { tile_n -= sp.n_tiles; ++grp_n; }
-        PackedHdr hn = packed_header(a.view[grp_n].packed, (unsigned)tile_n);
+        int4 hn = raw_header(a.view[grp_n].packed, tile_n);  // kept as loaded: three registers
         for (int u = blockIdx.x; u < sp.n_units; u += stride) {
-            const PackedHdr hdr = hn;
+            const int4 hdr = hn;
             const int grp = grp_n, tile = tile_n;
             tile_n += stride;
             while (tile_n >= sp.n_tiles) { tile_n -= sp.n_tiles; ++grp_n; }
-            if (u + stride < sp.n_units) hn = packed_header(a.view[grp_n].packed, (unsigned)tile_n);
+            if (u + stride < sp.n_units) hn = raw_header(a.view[grp_n].packed, tile_n);
             const UnitGeom g = unit_geom<M>(hdr, sp.zero_border, src_cols, src_rows);
             if (!g.fast) continue;
             const int ty = tile / sp.tiles_x, tx = tile - ty * sp.tiles_x;
@@ -168,15 +224,22 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
         }
     };
 
+    // Tiles that are not staged are only noted (s_slow) while the CTA streams; they are gathered per pixel afterwards,
+    // outside the streaming loop, whose registers the gather code would otherwise claim (the prefetched header and entries
+    // ended up in local memory).  A full list ends the streaming phase early; the outer loop resumes it after the drain.
+    int2* const s_slow = reinterpret_cast<int2*>(smem + SLay<M, CTAS>::kOffSlow);
     int n = 0, st = 0;
     uint32_t ph = 0;
     int grp_n = 0, tile_n = blockIdx.x;  // unit = (map group, tile); blockIdx.x < n_units
     while (tile_n >= sp.n_tiles) { tile_n -= sp.n_tiles; ++grp_n; }
-    PackedHdr hn = packed_header(a.view[grp_n].packed, (unsigned)tile_n);
+    int u = blockIdx.x;
+  for (;;) {
+    int n_slow = 0;
+    int4 hn = raw_header(a.view[grp_n].packed, tile_n);  // kept as loaded: three registers
     uint32_t en[kPx];
     load_entries(grp_n, tile_n, en);
-    for (int u = blockIdx.x; u < sp.n_units; u += stride) {
-        const PackedHdr hdr = hn;
+    for (; u < sp.n_units && n_slow < kSlowCap; u += stride) {
+        const int4 hdr = hn;
         uint32_t e[kPx];
 #pragma unroll
         for (int k = 0; k < kPx; ++k) e[k] = en[k];
@@ -184,48 +247,14 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
         tile_n += stride;
         while (tile_n >= sp.n_tiles) { tile_n -= sp.n_tiles; ++grp_n; }
         if (u + stride < sp.n_units) {  // the next tile's header and entries travel while this one is sampled
-            hn = packed_header(a.view[grp_n].packed, (unsigned)tile_n);
+            hn = raw_header(a.view[grp_n].packed, tile_n);
             load_entries(grp_n, tile_n, en);
         }
         const UnitGeom g = unit_geom<M>(hdr, sp.zero_border, src_cols, src_rows);
 
-        if (!g.fast) {  // per-pixel gather from global memory with full border handling (rare tiles)
-            const ViewArgs& mv = a.view[grp];
-            const int ty = tile / sp.tiles_x, tx = tile - ty * sp.tiles_x;
-            const int x0 = tx * kTileW, y0 = ty * M::kTileH;
-#pragma unroll 1
-            for (int k = 0; k < kPx; ++k) {
-                const int i = x0 + lane, j = y0 + kPx * sw + k;
-                if (i >= a.W || j >= a.H) continue;
-                int qx, qy;
-                if (hdr.flags & kHdrPackable) {
-                    qx = ((hdr.mnx + (int)(e[k] & 255u)) << M::kShift) | (int)((e[k] >> 16) & 31u);
-                    qy = ((hdr.mny + (int)((e[k] >> 8) & 255u)) << M::kShift) | (int)((e[k] >> 21) & 31u);
-                } else {
-                    qx = M::quant(__ldg(mv.xmap + (long long)j * mv.map_pitch + i));
-                    qy = M::quant(__ldg(mv.ymap + (long long)j * mv.map_pitch + i));
-                }
-                for (int f = 0; f < a.n_frames; ++f) {
-                    uint8_t* drow = a.dst + (long long)f * a.dst_frame_stride + (long long)j * a.dst_pitch;
-                    for (int v = grp; v < grp + nv; ++v) {
-                        const ViewArgs& vw = a.view[v];
-                        Src s{vw.src + (long long)f * vw.frame_stride, vw.rows, vw.cols, vw.pitch};
-                        int px[3];
-                        if (M::kInterp == VR180_INTER_NEAREST)
-                            fetch_tap<3>(s, sat16(qx), sat16(qy), a.border_mode, a.bv, px);
-                        else if (M::kInterp == VR180_INTER_LINEAR)
-                            sample_linear<3>(s, qx, qy, a.border_mode, a.bv, px);
-                        else if (M::kInterp == VR180_INTER_CUBIC)
-                            sample_tab<3, 4>(s, qx, qy, sp.tab, a.border_mode, a.bv, px);
-                        else
-                            sample_tab<3, 8>(s, qx, qy, sp.tab, a.border_mode, a.bv, px);
-                        uint8_t* o = drow + (long long)(vw.dst_x_offset + i) * 3;
-                        o[0] = (uint8_t)px[0];
-                        o[1] = (uint8_t)px[1];
-                        o[2] = (uint8_t)px[2];
-                    }
-                }
-            }
+        if (!g.fast) {
+            if (tid == 0) s_slow[n_slow] = make_int2(grp, tile);
+            ++n_slow;
             continue;
         }
 
@@ -235,16 +264,16 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
         for (int k = 0; k < kPx; ++k) {
             const int dx = (int)(e[k] & 255u), dy = (int)((e[k] >> 8) & 255u);  // iy - kLo - ry0 == dy
             M::set_offset(pc[k], dy * g.pitch + 3 * dx + g.org, true);
-            if constexpr (SLay<M>::kWeightTab != 0) {
+            if constexpr (SLay<M, CTAS>::kWeightTab != 0) {
                 asm("ld.shared.v2.u32 {%0, %1}, [%2];"
                     : "=r"(pc[k].W01), "=r"(pc[k].W23)
-                    : "r"(s_stage + SLay<M>::kOffTab + ((e[k] >> 13) & (1023u << 3))));
+                    : "r"(s_stage + SLay<M, CTAS>::kOffTab + ((e[k] >> 13) & (1023u << 3))));
             } else {
                 M::weights(pc[k], (int)((e[k] >> 16) & 31u), (int)((e[k] >> 21) & 31u), sp.tab);
             }
         }
         if constexpr (M::kWeightSmem != 0) {  // Lanczos4: the pixel's 64 weights, private copy in shared memory
-            uint8_t* slot = smem + SLay<M>::kOffW + tid * 16;
+            uint8_t* slot = smem + SLay<M, CTAS>::kOffW + tid * 16;
 #pragma unroll
             for (int ky = 0; ky < 8; ++ky)
                 *reinterpret_cast<uint4*>(slot + ky * (kSamplers * 16)) = __ldg(reinterpret_cast<const uint4*>(pc[0].w) + ky);
@@ -276,9 +305,22 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
             if (++st == kSlots) { st = 0; ph ^= 1u; }
         }
     }
+    // ---- drain: per-pixel gather of the noted tiles (sampling warps only: named barrier 1) ----
+    if (n_slow == 0 && u >= sp.n_units) break;  // the common case: nothing noted
+    asm volatile("bar.sync 1, %0;" ::"n"(kSamplers) : "memory");
+    for (int i = 0; i < n_slow; ++i) {
+        const int2 gt = s_slow[i];
+        const int4 hdr = raw_header(a.view[gt.x].packed, gt.y);
+        Entries<kPx> ev;
+        load_entries(gt.x, gt.y, ev.e);
+        gather_tile<M>(a, sp, gt.x, gt.y, nv, (hdr.z & kHdrPackable) != 0, (short)(hdr.x & 0xffff), (short)(hdr.y & 0xffff), ev);
+    }
+    if (u >= sp.n_units) break;
+    asm volatile("bar.sync 1, %0;" ::"n"(kSamplers) : "memory");  // the list is rewritten by the next streaming phase
+  }
 }
 
-template <class M>
+template <class M, int CTAS>
 static int launch_stream_mode(const RemapArgs& a, const short* tab, cudaStream_t st) {
     const int n_groups = a.share_map ? 1 : a.n_views;
     const TmaMaps* tm = tma_maps_for(a, M::kInterp, M::kRowsMin, M::kTileH, 1);
@@ -287,7 +329,7 @@ static int launch_stream_mode(const RemapArgs& a, const short* tab, cudaStream_t
     int dev = 0;
     VR180_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !attr_done[dev].load(std::memory_order_acquire)) {
-        VR180_CUDA(cudaFuncSetAttribute(k_warp_stream<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLay<M>::kSmemBytes));
+        VR180_CUDA(cudaFuncSetAttribute(k_warp_stream<M, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLay<M, CTAS>::kSmemBytes));
         attr_done[dev].store(1, std::memory_order_release);
     }
     static std::atomic<int> sm_count[64];
@@ -306,9 +348,9 @@ static int launch_stream_mode(const RemapArgs& a, const short* tab, cudaStream_t
     sp.zero_border = (a.border_mode == VR180_BORDER_CONSTANT && !(a.bv[0] | a.bv[1] | a.bv[2])) ? 1 : 0;
     sp.tab = tab;
     const int forced = g_debug_stream_grid.load(std::memory_order_relaxed);  // vr180_debug_set(3, n): tests
-    int grid = forced > 0 ? forced : sms * kStreamCtas;
+    int grid = forced > 0 ? forced : sms * CTAS;
     if (grid > sp.n_units) grid = sp.n_units;
-    k_warp_stream<M><<<grid, kThreads, SLay<M>::kSmemBytes, st>>>(a, sp, *tm);
+    k_warp_stream<M, CTAS><<<grid, kThreads, SLay<M, CTAS>::kSmemBytes, st>>>(a, sp, *tm);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     VR180_CUDA(cudaGetLastError());
     return VR180_OK;
@@ -320,10 +362,12 @@ static int launch_stream_mode(const RemapArgs& a, const short* tab, cudaStream_t
 // of this interpolation, no per-frame radius).
 int launch_remap_stream(const RemapArgs& a, int interp, const short* weight_tab, cudaStream_t st) {
     using namespace tiled;
-    if (interp == VR180_INTER_NEAREST) return launch_stream_mode<Nearest>(a, nullptr, st);
-    if (interp == VR180_INTER_LINEAR) return launch_stream_mode<LinearP>(a, nullptr, st);
-    if (interp == VR180_INTER_CUBIC) return launch_stream_mode<Cubic>(a, weight_tab, st);
-    if (interp == VR180_INTER_LANCZOS4) return launch_stream_mode<Lanczos4>(a, weight_tab, st);
+    if (interp == VR180_INTER_NEAREST) return launch_stream_mode<Nearest, kStreamCtas>(a, nullptr, st);
+    if (interp == VR180_INTER_LINEAR)
+        return (tiled_debug_flags() & 8) ? launch_stream_mode<LinearP, 4>(a, nullptr, st)
+                                         : launch_stream_mode<LinearP, kStreamCtas>(a, nullptr, st);
+    if (interp == VR180_INTER_CUBIC) return launch_stream_mode<Cubic, kStreamCtas>(a, weight_tab, st);
+    if (interp == VR180_INTER_LANCZOS4) return launch_stream_mode<Lanczos4, kStreamCtas>(a, weight_tab, st);
     return VR180_ERR_UNSUPPORTED;
 }
 
