@@ -360,8 +360,8 @@ def run_workload(torch, V, wl_name: str, wl: dict, steps: int, warmup: int, dist
     step()
     launches_per_step = lib.vr180_launch_count() - l0
     graphs = None
-    if pairs == 1:
-        # a single small pair per step is launch-bound from Python (ctypes call + 25 KB of kernel parameters ~ the kernel's
+    if pairs * n * n <= 72e6:
+        # a single pair (or a few small ones) per step is launch-bound from Python (ctypes call + 25 KB of kernel parameters ~ the kernel's
         # own duration): the step is captured once per ring slot in a CUDA graph and replayed, as a video loop would
         torch.cuda.synchronize()
         cap = torch.cuda.Stream(device)
@@ -370,7 +370,7 @@ def run_workload(torch, V, wl_name: str, wl: dict, steps: int, warmup: int, dist
             for k in range(ring):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=cap):
-                    wp(left[k:k + 1], right[k:k + 1], out=out[k:k + 1])
+                    wp(left[k * pairs:(k + 1) * pairs], right[k * pairs:(k + 1) * pairs], out=out[k * pairs:(k + 1) * pairs])
                 graphs.append(g)
         torch.cuda.synchronize()
 

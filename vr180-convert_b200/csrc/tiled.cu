@@ -1060,14 +1060,18 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
         n_dyn += (a0.view[g].map_kind == VR180_MAPSRC_ANALYTIC && a0.view[g].radius_dev) ? 1 : 0;
     if (n_dyn != 0 && n_dyn != n_groups) return VR180_ERR_UNSUPPORTED;
     const bool dyn = n_dyn != 0;
-    // One or two frames per launch with tile-packed LUTs: nothing to amortise a tile's prologue over -> persistent CTAs
-    // that stream the tiles (stream.cu).  VR180_TILED_DEBUG bit 1: whenever eligible; bit 2: never.
+    // A few frames per launch with tile-packed LUTs: little to amortise a tile's prologue over -> persistent CTAs that
+    // stream the tiles (stream.cu).  Measured, B200, (frame, eye) items per tile: 4K pairs sharing a map 2 / 4 / 8 / 16 / 32
+    // items 24.6 / 37.9 / 64.3 / 115.8 / 218.6 us streamed vs 36.3 / 45.7 / 78.5 / 115.7 / 196.8 us batched; 8K pairs with
+    // per-eye maps 1 / 2 / 4 items 108 / 153 / 258 us vs 217 / 245 / 310 us.  VR180_TILED_DEBUG bit 1: whenever eligible;
+    // bit 2: never.
+    constexpr int kStreamMaxItems = 12;
     {
         bool all_packed = !dyn;
         for (int g = 0; g < n_groups; ++g) all_packed = all_packed && a0.view[g].packed != nullptr;
         const int dbg = tiled_debug_flags();
         const int items = a0.n_frames * (a0.share_map ? a0.n_views : 1);
-        if (all_packed && !(dbg & 4) && ((dbg & 2) || items <= 4) && g_debug_frames_per_cta.load(std::memory_order_relaxed) <= 0) {
+        if (all_packed && !(dbg & 4) && ((dbg & 2) || items <= kStreamMaxItems) && g_debug_frames_per_cta.load(std::memory_order_relaxed) <= 0) {
             const int rc = launch_remap_stream(a0, interp, weight_tab, st);
             if (rc != VR180_ERR_UNSUPPORTED) return rc;
         }
