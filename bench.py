@@ -63,6 +63,9 @@ WORKLOADS = {
     "4k_pair_lut_linear": dict(n=2048, interp=1, tuple_=False, chain="base", src="lut_packed", radius="fixed", pairs=1,
                                desc="single 4K pair, cached tile-packed LUT instead of the FP64 chain (the per-frame path "
                                     "of a video loop) [BASELINE configs[1]]"),
+    "8k_pair_lut_linear": dict(n=4096, interp=1, tuple_=True, chain="rot_poly", src="lut_packed", radius="fixed", pairs=1,
+                               desc="ONE 8K pair per launch (2x4096^2 -> 8192x4096), per-eye rotation + PolynomialScaler, cached "
+                                    "tile-packed LUTs: the tile-streaming kernel [BASELINE configs[2], unbatched video loop]"),
     "8k_nearest_fixed": dict(n=4096, interp=0, tuple_=False, chain="base", src="analytic", radius="fixed", pairs=16,
                              desc="batched 8K pairs, base chain, fused analytic, INTER_NEAREST, fixed radius (the pipeline "
                                   "without the interpolation arithmetic)"),
@@ -587,7 +590,9 @@ def run_gpu(args) -> dict:
                      "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                      "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                      "algorithmic_bytes_per_launch": main["bytes_per_step"],
-                     "source_touched_fraction": main["touched_fraction"], "kernel": "vr180::tiled::k_warp_tiled (1 launch per step)"},
+                     "source_touched_fraction": main["touched_fraction"],
+                     "kernel": "vr180::tiled::k_warp_tiled (1 launch per step; k_warp_stream for <= 12 (frame, eye) items "
+                               "per tile with tile-packed LUTs)"},
         "e2e": None,
         "clocks": clocks,
     }

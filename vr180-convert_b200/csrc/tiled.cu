@@ -74,7 +74,9 @@ struct TileGeom {
 //   oempty[o]  (1)             the producer arrives as soon as the store that used out buffer o has finished
 //                              reading it (bulk wait_group.read); the sampling warps wait before rewriting it
 //                              (item n - OB), so a warp can run at most OB items ahead of the slowest one
-template <class M, int NV, bool DYN, int FR>  // FR: frames per item (2: one box load / tile store / barrier round per 2 frames)
+// SPLIT: the descriptors' boxes are ONE frame deep (a launch with per-frame radii needs those for its mixed chunks), so
+// an FR-frame item of an equal-radii chunk is fetched and stored as FR boxes on the same barrier / in the same bulk group.
+template <class M, int NV, bool DYN, int FR, bool SPLIT = false>  // FR: frames per item (2: one box load / tile store / barrier round per 2 frames)
 __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm, int v_begin, int f0, int f1,
                                            const typename M::Pixel (&pc)[M::kPx], const TileGeom& tg, const int pitch,
                                            uint8_t* smem, int band, int cg, const DynRadius& dr,
@@ -94,8 +96,10 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     const int n_items = ((f1 - f0 + FR - 1) / FR) * NV;
     const int rsel = tg.nrows <= M::kRowsMin ? 0 : (tg.nrows - M::kRowsMin + kRowsStep - 1) / kRowsStep;
     const int rect_bytes = (M::kRowsMin + rsel * kRowsStep) * pitch;  // one frame's box; multiple of 64
-    const int stage_bytes = FR * rect_bytes;                          // bytes one TMA box load delivers
-    const int stage_stride = (stage_bytes + 127) & ~127;              // TMA destinations are 128-byte aligned
+    const int stage_bytes = FR * rect_bytes;                          // bytes the box load(s) of an item deliver
+    // distance of an item's frames inside a stage: packed by a box FR frames deep; one-frame boxes land 128-byte aligned
+    const int frame_pitch = SPLIT ? (rect_bytes + 127) & ~127 : rect_bytes;
+    const int stage_stride = (FR * frame_pitch + 127) & ~127;         // TMA destinations are 128-byte aligned
     const int S = min(kMaxStages, Lay<M>::kStageArea / stage_stride);
 
     if (warp == kSamplers / 32) {  // ---- producer ----
@@ -122,7 +126,14 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
                 s_org[p_stage] = make_int2(bx0, ry0);  // released to the samplers by the arrive below
             }
             mbar_expect_tx(bar, (uint32_t)stage_bytes);
-            tma_load_3d(s_stage + p_stage * stage_stride, map0 + v * (kWidths * kRowSizes), bx0, ry0, f, bar);
+            if (SPLIT) {
+#pragma unroll
+                for (int fr = 0; fr < FR; ++fr)  // a frame past the batch is all zero fill, and still rect_bytes on the barrier
+                    tma_load_3d(s_stage + p_stage * stage_stride + fr * frame_pitch, map0 + v * (kWidths * kRowSizes), bx0, ry0,
+                                f + fr, bar);
+            } else {
+                tma_load_3d(s_stage + p_stage * stage_stride, map0 + v * (kWidths * kRowSizes), bx0, ry0, f, bar);
+            }
             ++p_item;
             if (++p_stage == S) p_stage = 0;
         };
@@ -132,7 +143,13 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
             const int v = (NV == 2) ? (n & 1) : 0, f = f0 + FR * ((NV == 2) ? (n >> 1) : n);
             mbar_wait(s_ofull + o * 8, (uint32_t)(n / OB) & 1u);  // every sampling warp has written item n
             if (n + S < n_items) load();  // ofull(n) also means: every warp has left the stage of item n -> re-fill it
-            tma_store_3d(&tm.dst, v ? dst_x1 : dst_x0, tg.y0, f, s_out + o * kOutItemBytes);
+            if (SPLIT) {
+#pragma unroll
+                for (int fr = 0; fr < FR; ++fr)
+                    tma_store_3d(&tm.dst, v ? dst_x1 : dst_x0, tg.y0, f + fr, s_out + o * kOutItemBytes + fr * kOutTileBytes);
+            } else {
+                tma_store_3d(&tm.dst, v ? dst_x1 : dst_x0, tg.y0, f, s_out + o * kOutItemBytes);
+            }
             bulk_commit();
             // hand the out buffer back as soon as the store has read it (the next ofull is an item time away, so
             // the producer has nothing else to do): a sampling warp may then run OB items ahead of the slowest one
@@ -202,7 +219,7 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
 #pragma unroll
             for (int k = 0; k < M::kPx; ++k) {
                 uint32_t r[FR];
-                sample_item<M, FR>(buf, (uint32_t)rect_bytes, pc[k], (uint32_t)pitch, r);
+                sample_item<M, FR>(buf, (uint32_t)frame_pitch, pc[k], (uint32_t)pitch, r);
 #pragma unroll
                 for (int fr = 0; fr < FR; ++fr) res[fr][k] = r[fr];
             }
@@ -211,7 +228,7 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
         for (int fr = 0; fr < FR; ++fr) {
             if (!DYN && M::kInterp != VR180_INTER_LANCZOS4) {
 #pragma unroll
-                for (int k = 0; k < M::kPx; ++k) res[fr][k] = M::sample(buf + fr * rect_bytes, pc[k], (uint32_t)pitch);
+                for (int k = 0; k < M::kPx; ++k) res[fr][k] = M::sample(buf + fr * frame_pitch, pc[k], (uint32_t)pitch);
             }
             // re-pack frame fr right away: its shuffles are in flight while the next frame is sampled
 #pragma unroll
@@ -522,8 +539,11 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     auto box_rows_of = [](int rows) {
         return M::kRowsMin + (rows <= M::kRowsMin ? 0 : (rows - M::kRowsMin + kRowsStep - 1) / kRowsStep) * kRowsStep;
     };
+    // (a chunk with varying radii runs one-frame items; FR-frame items of a DYN launch are FR one-frame boxes, each 128-byte aligned)
+    const int fr_item = dynr ? 1 : FR;
     auto stage_fits = [&](int rows, int pitch_bytes) {
-        return ((FR * box_rows_of(rows) * pitch_bytes + 127) & ~127) <= Lay<M>::kStageArea;
+        const int rect = box_rows_of(rows) * pitch_bytes;
+        return ((fr_item * (DYN ? (rect + 127) & ~127 : rect) + 127) & ~127) <= Lay<M>::kStageArea;
     };
     // Any other border (a colour, REPLICATE, REFLECT, WRAP, REFLECT_101) needs real taps or the border colour where the
     // footprint leaves the source: those tiles take the per-pixel path below; tiles inside the source never see a border.
@@ -682,8 +702,9 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         if (nv == 2) frame_loop<M, 2, DYN, 1>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
         else         frame_loop<M, 1, DYN, 1>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
     } else {
-        if (nv == 2) frame_loop<M, 2, false, FR>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
-        else         frame_loop<M, 1, false, FR>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
+        // (a DYN launch has one-frame boxes: its equal-radii chunks run FR-frame items as FR boxes each)
+        if (nv == 2) frame_loop<M, 2, false, FR, DYN>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
+        else         frame_loop<M, 1, false, FR, DYN>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
     }
 }
 
@@ -983,7 +1004,7 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
                        cudaStream_t st) {
     using namespace tiled;
     const int n_groups = a0.share_map ? 1 : a0.n_views;
-    const TmaMaps* tmp = tma_maps_for(a0, M::kInterp, M::kRowsMin, M::kTileH, FR);
+    const TmaMaps* tmp = tma_maps_for(a0, M::kInterp, M::kRowsMin, M::kTileH, DYN ? 1 : FR);
     if (!tmp) return VR180_ERR_UNSUPPORTED;
     const TmaMaps& tm = *tmp;
 
@@ -1083,23 +1104,32 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
     const long long tiles = (long long)((a0.W + tiled::kTileW - 1) / tiled::kTileW) * ((a0.H + tile_h - 1) / tile_h) * n_groups;
     const int vpc = a0.share_map ? a0.n_views : 1;
     const bool pairs = !dyn && frames_per_cta(tiles, a0.n_frames, vpc) >= 2;
+    // per-frame radii: chunks whose frames all share one radius (a static rig) run the same multi-frame items
+    const bool pairs_dyn = dyn && frames_per_cta(tiles, a0.n_frames, vpc) >= 2;
     if (interp == VR180_INTER_NEAREST) {
-        if (dyn) return launch_mode<tiled::Nearest, true, 1>(a0, c0, c1, nullptr, st);
+        if (dyn) return pairs_dyn ? launch_mode<tiled::Nearest, true, 2>(a0, c0, c1, nullptr, st)
+                                  : launch_mode<tiled::Nearest, true, 1>(a0, c0, c1, nullptr, st);
         return pairs ? launch_mode<tiled::Nearest, false, 2>(a0, c0, c1, nullptr, st)
                      : launch_mode<tiled::Nearest, false, 1>(a0, c0, c1, nullptr, st);
     }
     if (interp == VR180_INTER_LINEAR) {  // LinearP: byte alignment by PRMT (5.8 % fewer instructions than Linear's funnel shifts)
-        if (dyn) return launch_mode<tiled::LinearP, true, 1>(a0, c0, c1, nullptr, st);
+        if (dyn) return pairs_dyn ? launch_mode<tiled::LinearP, true, 2>(a0, c0, c1, nullptr, st)
+                                  : launch_mode<tiled::LinearP, true, 1>(a0, c0, c1, nullptr, st);
         return pairs ? launch_mode<tiled::LinearP, false, 2>(a0, c0, c1, nullptr, st)
                      : launch_mode<tiled::LinearP, false, 1>(a0, c0, c1, nullptr, st);
     }
     if (!weight_tab) return VR180_ERR_UNSUPPORTED;
     if (interp == VR180_INTER_LANCZOS4) {
-        if (dyn) return launch_mode<tiled::Lanczos4, true, 1>(a0, c0, c1, weight_tab, st);
+        if (dyn) return pairs_dyn ? launch_mode<tiled::Lanczos4, true, 2>(a0, c0, c1, weight_tab, st)
+                                  : launch_mode<tiled::Lanczos4, true, 1>(a0, c0, c1, weight_tab, st);
         return pairs ? launch_mode<tiled::Lanczos4, false, 2>(a0, c0, c1, weight_tab, st)
                      : launch_mode<tiled::Lanczos4, false, 1>(a0, c0, c1, weight_tab, st);
     }
-    if (dyn) return launch_mode<tiled::Cubic, true, 1>(a0, c0, c1, weight_tab, st);
+    if (dyn) {
+        if (frames_per_cta(tiles, a0.n_frames, vpc) >= 8) return launch_mode<tiled::Cubic, true, 4>(a0, c0, c1, weight_tab, st);
+        return pairs_dyn ? launch_mode<tiled::Cubic, true, 2>(a0, c0, c1, weight_tab, st)
+                         : launch_mode<tiled::Cubic, true, 1>(a0, c0, c1, weight_tab, st);
+    }
     if (frames_per_cta(tiles, a0.n_frames, vpc) >= 8) return launch_mode<tiled::Cubic, false, 4>(a0, c0, c1, weight_tab, st);
     return pairs ? launch_mode<tiled::Cubic, false, 2>(a0, c0, c1, weight_tab, st)
                  : launch_mode<tiled::Cubic, false, 1>(a0, c0, c1, weight_tab, st);
