@@ -890,6 +890,7 @@ static EncodeTiledFn encode_tiled_fn() {
 
 // uint8 tensor (row_bytes, rows, frames) with byte strides (pitch, frame_stride); box (box_w, box_h, 1).
 // Out-of-bounds box elements are filled with zeros on loads and dropped on stores.
+int tiled_debug_flags();
 static bool encode_u8_3d(CUtensorMap* out, const void* base, long long row_bytes, long long rows, long long frames,
                          long long pitch, long long frame_stride, int box_w, int box_h, int box_d) {
     EncodeTiledFn fn = encode_tiled_fn();
@@ -899,8 +900,11 @@ static bool encode_u8_3d(CUtensorMap* out, const void* base, long long row_bytes
     const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
     const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_d};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
+    // VR180_TILED_DEBUG bits 4-5 (experiment): L2 promotion of the boxes' sectors -- 0: 128 B (default), 1: none, 2: 64 B, 3: 256 B
+    static const CUtensorMapL2promotion promo[4] = {CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B};
     return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo[(tiled_debug_flags() >> 4) & 3],
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
