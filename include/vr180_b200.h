@@ -192,13 +192,18 @@ int vr180_pack_lut(const float* xmap_dev, const float* ymap_dev, int64_t map_pit
 /* ------------------------------------------------------------------------------------------------------
  * (2a') tile-packed LUT -- the cached-LUT form the tiled kernel reads with one 128-bit load per thread.
  *      For every output tile of the requested interpolation (32 x 32 px NEAREST / LINEAR, 32 x 16 CUBIC, 32 x 8
- *      LANCZOS4) it stores a 16-byte header {min ix, max ix, min iy, max iy (int16), packable flag} and one uint32
+ *      LANCZOS4) it stores a 16-byte header {min ix, max ix, min iy, max iy (int16), flags} and one uint32
  *      per pixel {ix - min ix : 8, iy - min iy : 8, ax : 5, ay : 5} in the order the kernel's threads consume them
  *      (thread-major), with (ix, iy, ax, ay) exactly the integers cv::remap derives from the float32 maps
  *      (sx = cvRound(x * 32), ix = sx >> 5, ax = sx & 31; NEAREST: ix = cvRound(x)) -- lossless w.r.t. the remap
  *      output.  4 bytes per pixel instead of 8, and the tile's source rectangle comes from the header instead of a
  *      block-wide reduction.  Tiles that cannot be packed (NaN / saturated coordinates, footprints wider than 255 px,
- *      partial edge tiles) are flagged and read the float32 maps instead.  Replaces the convertMaps step inside
+ *      partial edge tiles) are flagged and read the float32 maps instead.  The header's flags also carry the geometry of
+ *      the tile's source rectangle (TMA box rows, and the box width = staged row pitch with the fewest shared-memory bank
+ *      conflicts for the tile's own tap addresses), chosen once here instead of in every launch: with it, launches of
+ *      one or a few frames stream the tiles through persistent CTAs whose producer warp fetches the next tiles'
+ *      rectangles from the headers alone (csrc/stream.cu).  The buffer's layout is private to one build of the library:
+ *      build it at run time with the library that consumes it, do not persist it.  Replaces the convertMaps step inside
  *      cv.remap at remapper.py:389 for apply()'s one-map-many-images loop (remapper.py:381-398).
  *      vr180_packed_lut_bytes: size of the device buffer for an out_w x out_h map.
  * ---------------------------------------------------------------------------------------------------- */
