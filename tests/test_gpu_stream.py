@@ -164,3 +164,27 @@ def test_stream_more_unstaged_tiles_than_the_list_holds(hooks):
     want = np.concatenate([cv2.remap(ln[0], m[0], m[1], interpolation=1, borderMode=cv2.BORDER_REPLICATE),
                            cv2.remap(rn[0], m[0], m[1], interpolation=1, borderMode=cv2.BORDER_REPLICATE)], axis=1)
     assert np.array_equal(got[0], want), int((got[0] != want).sum())
+
+
+def test_auto_map_source_switches_to_the_cached_lut_on_the_second_small_call(hooks):
+    """SbsWarper's default map_source="auto": batches and the first small call are analytic; from the second small call
+    on the plan serves one- / two-pair calls from its tile-packed LUT (streaming kernel); auto radius stays analytic."""
+    import torch
+
+    rng = np.random.default_rng(12)
+    ln = rng.integers(0, 256, (7, HIN, WIN, 3), dtype=np.uint8)
+    rn = rng.integers(0, 256, (7, HIN, WIN, 3), dtype=np.uint8)
+    left, right = torch.from_numpy(ln).cuda(), torch.from_numpy(rn).cuda()
+    want = _want(ln, rn, 1, False, 130.0)
+    wp = V.SbsWarper(_chain(QL), size_input=(HIN, WIN), size_output=(WOUT, HOUT), interpolation=1, radius=130.0)
+    assert wp.map_source == "auto"
+    assert np.array_equal(wp(left[:1], right[:1]).cpu().numpy(), want[:1]) and wp._packed is None  # analytic
+    assert np.array_equal(wp(left, right).cpu().numpy(), want) and wp._packed is None              # a batch: analytic
+    assert np.array_equal(wp(left[1:3], right[1:3]).cpu().numpy(), want[1:3]) and wp._packed is not None
+    n0 = _launches()
+    assert np.array_equal(wp(left[3:4], right[3:4]).cpu().numpy(), want[3:4])
+    assert _launches() - n0 == 1
+    auto = V.SbsWarper(_chain(QL), size_input=(HIN, WIN), size_output=(WOUT, HOUT), interpolation=1, radius="auto")
+    for _ in range(3):
+        auto(left[:1], right[:1])
+    assert auto._packed is None

@@ -8,6 +8,10 @@ HBM (torch CUDA tensors are only the buffer type) is warped by one kernel launch
   * map_source="lut":      float32 maps built once (k_build_map, or the host for opaque transformers), cached;
   * map_source="lut_fixed": the maps quantised once to cv2's fixed-point (k_pack_lut), cached;
   * map_source="lut_packed": the tile-packed 4-byte LUT (k_pack_tiles): one 128-bit load per thread, cached;
+  * map_source="auto" (default): "analytic" for batches; a plan with a fixed radius that is called again and again
+    with one or a few pairs (a frame-at-a-time video loop) builds the tile-packed LUT on its second such call and
+    serves them from it -- vr180_remap then streams the tiles through persistent CTAs (csrc/stream.cu): a 4K pair
+    takes 25 us instead of 60 us, an 8K pair 110 us instead of ~300 us.  Costs 12 bytes of HBM per output pixel and map;
   * radius="auto": k_get_radius per frame (max over the two eyes) feeds the warp kernel through device memory.
 
 Frames of a clip are independent, so multi-GPU runs shard them statically with `shard_range` (no collective).
@@ -39,7 +43,7 @@ class SbsWarper:
         boarder_mode: int = BORDER_CONSTANT,
         boarder_value: Any = 0,
         radius: float | Sequence[float] | Literal["auto", "max"] = "max",
-        map_source: Literal["analytic", "lut", "lut_fixed", "lut_packed"] = "analytic",
+        map_source: Literal["auto", "analytic", "lut", "lut_fixed", "lut_packed"] = "auto",
         channels: int = 3,
         threshold: float = 10,
         device: Any = None,
@@ -56,9 +60,12 @@ class SbsWarper:
         self.border_value = _border_bytes(boarder_value, channels)
         self.channels = channels
         self.threshold = float(threshold)
+        if map_source not in ("auto", "analytic", "lut", "lut_fixed", "lut_packed"):
+            raise ValueError(f"unknown map_source {map_source!r}")
         self.map_source = map_source
+        self._small_calls = 0  # "auto": calls with <= _STREAM_ITEMS (frame, eye) items per tile so far
         self.auto_radius = isinstance(radius, str) and radius == "auto"
-        if self.auto_radius and map_source != "analytic":
+        if self.auto_radius and map_source not in ("analytic", "auto"):
             raise ValueError('radius="auto" per frame is consumed on the device by the analytic kernel only')
         if isinstance(radius, str) and radius == "max":
             radius = min(self.rows / 2, self.cols / 2)
@@ -71,8 +78,11 @@ class SbsWarper:
         self.radii = radii
         self._lowered = [lower_full(t, radius=r, size_input=(self.rows, self.cols), size_output=(self.w, self.h))
                          for t, r in zip(self.transformers, radii)]
-        if map_source == "analytic" and any(o is None for o in self._lowered):
+        self._lowerable = all(o is not None for o in self._lowered)
+        if map_source == "analytic" and not self._lowerable:
             raise ValueError("transformer has no lowering (user-defined Python class): use map_source='lut'")
+        if self.auto_radius and not self._lowerable:
+            raise ValueError('radius="auto" per frame needs a lowerable transformer (the analytic kernel consumes it)')
         if map_source == "lut_fixed" and self.interpolation == INTER_NEAREST:
             raise ValueError("the fixed-point LUT stores x*32; INTER_NEAREST needs map_source='lut' or 'analytic'")
         self._chains = [N.make_chain(o) if o is not None else None for o in self._lowered]
@@ -133,6 +143,22 @@ class SbsWarper:
         return self._packed
 
     # --- per batch ---------------------------------------------------------------------------------------
+    _STREAM_ITEMS = 12  # (frame, eye) items per tile up to which vr180_remap streams the tiles (csrc/tiled.cu)
+
+    def _source_for(self, n_frames: int) -> str:
+        """The coordinate source of one call: the plan's, or for "auto" the faster one for this batch size."""
+        if self.map_source != "auto":
+            return self.map_source
+        has_tiled_lut = self.channels == 3
+        if not self._lowerable:  # user-defined Python transformer: host maps, once
+            return "lut_packed" if has_tiled_lut else "lut"
+        if self.auto_radius or not has_tiled_lut:
+            return "analytic"
+        if n_frames * (2 if self.share_map else 1) > self._STREAM_ITEMS:
+            return "analytic"
+        self._small_calls += 1  # the first small call is not worth a LUT yet (a plan used once)
+        return "lut_packed" if self._small_calls > 1 or self._packed is not None else "analytic"
+
     def _image(self, t) -> N.Image:
         if t.dtype != self.torch.uint8 or t.dim() != 4 or t.shape[1] != self.rows or t.shape[2] != self.cols \
                 or t.shape[3] != self.channels or t.stride(3) != 1 or t.stride(2) != self.channels:
@@ -180,20 +206,21 @@ class SbsWarper:
             radius_dev = radius
         elif self.auto_radius:
             radius_dev, _ = self.radius_per_frame(left, right)
+        source = self._source_for(n)
         for v, frames in enumerate((left, right)):
             vw = p.view[v]
             vw.src = self._image(frames)
             vw.dst_x_offset = v * self.w
             m = 0 if self.share_map else v
-            if self.map_source == "analytic":
+            if source == "analytic":
                 vw.map.kind = N.MAPSRC_ANALYTIC
                 vw.map.chain = C.pointer(self._chains[m])
                 vw.map.radius_dev = radius_dev.data_ptr() if radius_dev is not None else None
-            elif self.map_source == "lut":
+            elif source == "lut":
                 maps = self.maps()
                 vw.map.kind = N.MAPSRC_FLOAT2
                 vw.map.xmap, vw.map.ymap, vw.map.map_pitch = maps[m, 0].data_ptr(), maps[m, 1].data_ptr(), self.w
-            elif self.map_source == "lut_packed":
+            elif source == "lut_packed":
                 maps, packed = self.maps(), self.packed_lut()
                 vw.map.kind = N.MAPSRC_PACKED
                 vw.map.xmap, vw.map.ymap, vw.map.map_pitch = maps[m, 0].data_ptr(), maps[m, 1].data_ptr(), self.w
