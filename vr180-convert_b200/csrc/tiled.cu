@@ -1096,7 +1096,9 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
         for (int g = 0; g < n_groups; ++g) all_packed = all_packed && a0.view[g].packed != nullptr;
         const int dbg = tiled_debug_flags();
         const int items = a0.n_frames * (a0.share_map ? a0.n_views : 1);
-        if (all_packed && !(dbg & 4) && ((dbg & 2) || items <= kStreamMaxItems) && g_debug_frames_per_cta.load(std::memory_order_relaxed) <= 0) {
+        const bool tab_ok = (interp != VR180_INTER_CUBIC && interp != VR180_INTER_LANCZOS4) || weight_tab != nullptr;
+        if (all_packed && tab_ok && !(dbg & 4) && ((dbg & 2) || items <= kStreamMaxItems) &&
+            g_debug_frames_per_cta.load(std::memory_order_relaxed) <= 0) {
             const int rc = launch_remap_stream(a0, interp, weight_tab, st);
             if (rc != VR180_ERR_UNSUPPORTED) return rc;
         }
