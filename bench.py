@@ -61,8 +61,9 @@ WORKLOADS = {
     "5k7_lutfixed_linear": dict(n=2880, interp=1, tuple_=False, chain="base", src="lut_fixed", radius="fixed", pairs=64,
                                 desc="as 5k7_lut_linear with the 8 B/px fixed-point LUT (int32 sx, sy)"),
     "4k_pair_lut_linear": dict(n=2048, interp=1, tuple_=False, chain="base", src="lut_packed", radius="fixed", pairs=1,
-                               desc="single 4K pair, cached tile-packed LUT instead of the FP64 chain (the per-frame path "
-                                    "of a video loop) [BASELINE configs[1]]"),
+                               desc="single 4K pair, cached tile-packed LUT instead of the FP64 chain: the per-frame path of a "
+                                    "video loop, what SbsWarper's default map_source='auto' serves from a plan's second "
+                                    "one-pair call on (tile-streaming kernel) [BASELINE configs[1]]"),
     "8k_pair_lut_linear": dict(n=4096, interp=1, tuple_=True, chain="rot_poly", src="lut_packed", radius="fixed", pairs=1,
                                desc="ONE 8K pair per launch (2x4096^2 -> 8192x4096), per-eye rotation + PolynomialScaler, cached "
                                     "tile-packed LUTs: the tile-streaming kernel [BASELINE configs[2], unbatched video loop]"),

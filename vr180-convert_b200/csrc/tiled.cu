@@ -87,7 +87,9 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     constexpr int kOutItemBytes = FR * kOutTileBytes;
     constexpr int OB = M::kOutTiles / FR < kOutBufs ? M::kOutTiles / FR : kOutBufs;  // out buffers of one item each
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t s_stage = smem_u32(smem), s_full = s_stage + Lay<M>::kOffBar;
+    uint32_t s_stage = smem_u32(smem);
+    asm volatile("" : "+r"(s_stage));  // opaque: otherwise the window base is re-derived (S2R SR_CgaCtaId + MOV + LEA) in every item
+    const uint32_t s_full = s_stage + Lay<M>::kOffBar;
     const uint32_t s_ofull = s_full + 2 * kMaxStages * 8, s_oempty = s_ofull + kOutBufs * 8, s_out = s_stage + Lay<M>::kOffOut;
 
     int2* const s_org = reinterpret_cast<int2*>(smem + Lay<M>::kOffOrg);
