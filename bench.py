@@ -600,12 +600,19 @@ def run_gpu(args) -> dict:
     if main.get("e2e"):
         e = dict(main["e2e"])
         ceiling, py = e["copy_ceiling"], main["e2e_python_api"]["value"]
+        slowest = ceiling
         if dist is not None:  # whole-job numbers: every rank ran its own pipeline / copy test at the same time
             tt = torch.tensor([ceiling, py], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.SUM)
-            ceiling, py = float(tt[0].item()), float(tt[1].item())
+            tm = torch.tensor([ceiling], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tm, op=dist.ReduceOp.MIN)
+            ceiling, py, slowest = float(tt[0].item()), float(tt[1].item()), float(tm[0].item())
+        # `value` is timed as the max over ranks, so the fair bound is world x the SLOWEST rank's copy rate (GPUs far from
+        # the host's memory get less of it); `copy_ceiling` (the sum of the ranks' rates) is the box's total
         e.update({"per_gpu_value": e["value"], "value": e["value"] * world, "copy_ceiling": ceiling,
                   "frac_of_ceiling": e["value"] * world / ceiling,
+                  "copy_ceiling_at_slowest_rank": slowest * world,
+                  "frac_of_ceiling_at_slowest_rank": e["value"] / slowest,
                   "h2d_bytes_per_step": e["h2d_bytes_per_step"] * world, "d2h_bytes_per_step": e["d2h_bytes_per_step"] * world})
         line["e2e"] = e
         line["e2e_python_api"] = {**main["e2e_python_api"], "per_gpu_value": main["e2e_python_api"]["value"], "value": py,
