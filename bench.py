@@ -519,6 +519,22 @@ def run_workload(torch, V, wl_name: str, wl: dict, steps: int, warmup: int, dist
                                  "api": "vr180_convert_b200.lr_frames(transformer, [ndarray...], [ndarray...]) on pageable "
                                         "NumPy arrays (apply_lr's in-memory part for a clip)",
                                  "vs_c_abi": (pe * n * 2 * n / 1e6 / dtp) / res["e2e"]["value"]}
+        # ... and with the frames in page-locked arrays from V.pinned_empty (what a capture / decode loop that owns its
+        # buffers would hand over): no packing copy, the Python layer's own overhead is what is left
+        lefts_p, rights_p = [], []
+        for i in range(pe):
+            for dst_list, src_arr in ((lefts_p, lefts[i]), (rights_p, rights[i])):
+                a_ = V.pinned_empty(src_arr.shape)
+                a_[...] = src_arr
+                dst_list.append(a_)
+
+        def py_step_pinned():
+            state_py["out"] = V.lr_frames(t, lefts_p, rights_p, size_output=(n, n), interpolation=wl["interp"], radius=py_radius)
+
+        dtq = timed_host(py_step_pinned, max(3, min(steps, 5)))
+        res["e2e_python_api"].update({"pinned_inputs_per_gpu_value": pe * n * 2 * n / 1e6 / dtq, "pinned_inputs_ms_per_step": dtq * 1e3,
+                                      "pinned_inputs_vs_c_abi": (pe * n * 2 * n / 1e6 / dtq) / res["e2e"]["value"]})
+        del lefts_p, rights_p
         res["e2e_python_frame0"] = np.array(state_py["out"][0])
         del lefts, rights, state_py
     del left, right, out, wp
