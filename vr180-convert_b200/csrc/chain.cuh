@@ -15,7 +15,11 @@
 // and converts only when the next op needs another form.  This leaves one acos + one sqrt + two divisions per
 // 3-D step instead of ~10 transcendental calls, and differs from the reference only by a few float64 roundings
 // (~1e-13 px), i.e. the float32 map is the same float32 except for a vanishing number of round-to-nearest ties
-// (SURVEY.md §7 hard part 1, Appendix A).  Operations the reference performs as separate NumPy ufuncs
+// (SURVEY.md §7 hard part 1, Appendix A).  The one exception is a projection's singular point falling exactly on an
+// output pixel (the stereographic antipode, 90 degrees off axis of the rectilinear mapping): one coordinate is ~1e17 px
+// and the other the product of a ~1e-17 direction cosine and that radius, so the two algebraically equal forms differ
+// by tens of pixels there; under the default constant border the pixel is the border colour either way
+// (tests/test_gpu_fuzz.py).  Operations the reference performs as separate NumPy ufuncs
 // (mul then add, Horner steps) use explicit __dmul_rn/__dadd_rn so no FMA contraction changes a rounding.
 #pragma once
 #include <cuda_runtime.h>
