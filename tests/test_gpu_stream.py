@@ -109,7 +109,7 @@ def test_stream_borders(hooks, interp, border):
 
 def test_stream_is_the_default_for_a_single_pair(hooks):
     """Without hooks a single pair with a packed LUT takes the streaming kernel (one launch, same result as the batch
-    kernel), and a 5-pair batch does not."""
+    kernel); a 5-pair batch of the same plan gives the same frames (streamed too: 10 items per tile)."""
     import torch
 
     rng = np.random.default_rng(5)
@@ -172,8 +172,8 @@ def test_auto_map_source_switches_to_the_cached_lut_on_the_second_small_call(hoo
     import torch
 
     rng = np.random.default_rng(12)
-    ln = rng.integers(0, 256, (7, HIN, WIN, 3), dtype=np.uint8)
-    rn = rng.integers(0, 256, (7, HIN, WIN, 3), dtype=np.uint8)
+    ln = rng.integers(0, 256, (11, HIN, WIN, 3), dtype=np.uint8)  # 11 pairs = 22 (frame, eye) items per tile: a batch
+    rn = rng.integers(0, 256, (11, HIN, WIN, 3), dtype=np.uint8)
     left, right = torch.from_numpy(ln).cuda(), torch.from_numpy(rn).cuda()
     want = _want(ln, rn, 1, False, 130.0)
     wp = V.SbsWarper(_chain(QL), size_input=(HIN, WIN), size_output=(WOUT, HOUT), interpolation=1, radius=130.0)

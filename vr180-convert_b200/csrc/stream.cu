@@ -37,9 +37,10 @@ struct SLay {
     static constexpr int kSlotBytes = kStreamSlotBytes<M>;
     static_assert(kSlots == 3, "kStreamSlotBytes (tiled.cuh) is a third of the staging area");
     static constexpr int kOutTileBytes = M::kTileH * kTileW * 3;
-    static constexpr int kOB = CTAS >= 4 ? 2 : kOutBufs;  // out buffers of one tile each
+    static constexpr int kOB = CTAS >= 4 ? 2 : kOutBufs;  // out buffers of one item each: the tile of one eye or of both
+    static constexpr int kOutItemBytes = 2 * kOutTileBytes;
     static constexpr int kOffOut = kSlots * kSlotBytes;
-    static constexpr int kOffBar = kOffOut + kOB * kOutTileBytes;  // full[kSlots], ofull[kOB], oempty[kOB]
+    static constexpr int kOffBar = kOffOut + kOB * kOutItemBytes;  // full[kSlots], ofull[kOB], oempty[kOB]
     static constexpr int kOffQ = (kOffBar + (kSlots + 2 * kOB) * 8 + 15) & ~15;  // int4 per slot: store coordinates of the item in it
     static constexpr int kOffW = (kOffQ + kSlots * 16 + 15) & ~15;
     // bilinear: the packed weight pairs {W01, W23} of all 32 x 32 sub-pixel positions, built once per CTA -- a tile's
@@ -63,6 +64,7 @@ __device__ __forceinline__ int4 raw_header(const void* packed, int tile) {
 }
 struct UnitGeom {
     int fast, bx0, ry0, pitch, rsel, rect_bytes, org;
+    int eye_pitch;  // distance of the two eyes' rectangles inside a slot (TMA destinations are 128-byte aligned)
 };
 template <class M>
 __device__ __forceinline__ UnitGeom unit_geom(const int4& raw, int zero_border, int src_cols, int src_rows) {
@@ -75,6 +77,7 @@ __device__ __forceinline__ UnitGeom unit_geom(const int4& raw, int zero_border, 
     g.pitch = kPitchMin + kPitchStep * ((h.flags >> 8) & 15);
     g.rsel = (h.flags >> 12) & 15;
     g.rect_bytes = (M::kRowsMin + g.rsel * kRowsStep) * g.pitch;
+    g.eye_pitch = (g.rect_bytes + 127) & ~127;
     constexpr int kAll = kHdrPackable | kHdrStageable | kHdrFitsSlot;
     g.fast = (h.flags & kAll) == kAll;
     if (!zero_border)  // any other border needs real taps where the footprint leaves the source: per-pixel path
@@ -139,6 +142,7 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
               const __grid_constant__ TmaMaps tm) {
     constexpr int kPx = M::kPx;
     constexpr int kOB = SLay<M, CTAS>::kOB, kOutTileBytes = SLay<M, CTAS>::kOutTileBytes, kSlotBytes = SLay<M, CTAS>::kSlotBytes;
+    constexpr int kOutItemBytes = SLay<M, CTAS>::kOutItemBytes;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s_stage = smem_u32(smem), s_full = s_stage + SLay<M, CTAS>::kOffBar;
@@ -169,7 +173,8 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
             const int o = n_store & (kOB - 1);
             mbar_wait(s_ofull + o * 8, (uint32_t)(n_store / kOB) & 1u);
             const int4 q = s_q[s_slot];
-            tma_store_3d(&tm.dst, q.x, q.y, q.z, s_out + o * kOutTileBytes);
+            tma_store_3d(&tm.dst, q.x, q.y, q.z, s_out + o * kOutItemBytes);
+            if (q.w >= 0) tma_store_3d(&tm.dst, q.w, q.y, q.z, s_out + o * kOutItemBytes + kOutTileBytes);  // the other eye
             bulk_commit();
             bulk_wait_read<0>();
             mbar_arrive(s_oempty + o * 8);
@@ -189,13 +194,26 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
             if (!g.fast) continue;
             const int ty = tile / sp.tiles_x, tx = tile - ty * sp.tiles_x;
             const CUtensorMap* const map0 = &tm.src[grp][(g.pitch - kPitchMin) / kPitchStep][g.rsel];
+            // Both eyes of a frame share the tile's coordinates: when their two rectangles fit one slot they travel as ONE
+            // item (two box loads on one barrier, one hand-shake with the sampling warps, two tile stores).
+            const bool pair = nv == 2 && 2 * g.eye_pitch <= kSlotBytes;
+            const int x_l = (a.view[grp].dst_x_offset + tx * kTileW) * 3;
+            const int x_r = nv == 2 ? (a.view[grp + 1].dst_x_offset + tx * kTileW) * 3 : -1;
             for (int f = 0; f < a.n_frames; ++f) {
-                for (int v = 0; v < nv; ++v) {
+                for (int v = 0; v < (pair ? 1 : nv); ++v) {
                     if (n_load - n_store == kSlots) store_next();
                     const uint32_t bar = s_full + l_slot * 8;
-                    s_q[l_slot] = make_int4((a.view[grp + v].dst_x_offset + tx * kTileW) * 3, ty * M::kTileH, f, 0);
-                    mbar_expect_tx(bar, (uint32_t)g.rect_bytes);
-                    tma_load_3d(s_stage + l_slot * kSlotBytes, map0 + v * (kWidths * kRowSizes), g.bx0, g.ry0, f, bar);
+                    const uint32_t dst = s_stage + l_slot * kSlotBytes;
+                    if (pair) {
+                        s_q[l_slot] = make_int4(x_l, ty * M::kTileH, f, x_r);
+                        mbar_expect_tx(bar, 2u * (uint32_t)g.rect_bytes);
+                        tma_load_3d(dst, map0, g.bx0, g.ry0, f, bar);
+                        tma_load_3d(dst + g.eye_pitch, map0 + kWidths * kRowSizes, g.bx0, g.ry0, f, bar);
+                    } else {
+                        s_q[l_slot] = make_int4(v ? x_r : x_l, ty * M::kTileH, f, -1);
+                        mbar_expect_tx(bar, (uint32_t)g.rect_bytes);
+                        tma_load_3d(dst, map0 + v * (kWidths * kRowSizes), g.bx0, g.ry0, f, bar);
+                    }
                     ++n_load;
                     if (++l_slot == kSlots) l_slot = 0;
                 }
@@ -283,30 +301,39 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
             pc[0].ws = smem_u32(slot);
         }
 
-        const int n_items = a.n_frames * nv;
+        const bool pair = nv == 2 && 2 * g.eye_pitch <= kSlotBytes;  // as the producer decides
+        auto item_loop = [&](auto eyes_tag, int n_items) {
+            constexpr int EYES = decltype(eyes_tag)::value;
 #pragma unroll 1
-        for (int it = 0; it < n_items; ++it) {
-            mbar_wait(s_full + st * 8, ph);
-            const uint32_t buf = s_stage + st * kSlotBytes;
-            uint32_t word[kPx];
+            for (int it = 0; it < n_items; ++it) {
+                mbar_wait(s_full + st * 8, ph);
+                const uint32_t buf = s_stage + st * kSlotBytes;
+                const int o = n & (kOB - 1);
+                const uint32_t ob = outp + o * kOutItemBytes;
 #pragma unroll
-            for (int k = 0; k < kPx; ++k) {
-                const uint32_t r = M::sample(buf, pc[k], (uint32_t)g.pitch);
-                word[k] = __byte_perm(r, __shfl_down_sync(0xffffffffu, r, 1), out_sel);
-            }
-            const int o = n & (kOB - 1);
-            if (n >= kOB) mbar_wait(s_oempty + o * 8, (uint32_t)(n / kOB + 1) & 1u);  // store n - kOB has read out[o]
-            if (flags & 1u) {
-                const uint32_t ob = outp + o * kOutTileBytes;
+                for (int v = 0; v < EYES; ++v) {
+                    uint32_t word[kPx];
 #pragma unroll
-                for (int k = 0; k < kPx; ++k) sts32(ob + k * (kTileW * 3), word[k]);
+                    for (int k = 0; k < kPx; ++k) {
+                        const uint32_t r = M::sample(buf + v * g.eye_pitch, pc[k], (uint32_t)g.pitch);
+                        word[k] = __byte_perm(r, __shfl_down_sync(0xffffffffu, r, 1), out_sel);
+                    }
+                    // (after the first eye's sampling, which does not need the out buffer yet)
+                    if (v == 0 && n >= kOB) mbar_wait(s_oempty + o * 8, (uint32_t)(n / kOB + 1) & 1u);  // store n - kOB has read out[o]
+                    if (flags & 1u) {
+#pragma unroll
+                        for (int k = 0; k < kPx; ++k) sts32(ob + v * kOutTileBytes + k * (kTileW * 3), word[k]);
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (flags & 2u) mbar_arrive(s_ofull + o * 8);  // this warp's rows of the item are in out[o]; it has left the slot
+                ++n;
+                if (++st == kSlots) { st = 0; ph ^= 1u; }
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (flags & 2u) mbar_arrive(s_ofull + o * 8);  // this warp's rows of the item are in out[o]; it has left the slot
-            ++n;
-            if (++st == kSlots) { st = 0; ph ^= 1u; }
-        }
+        };
+        if (pair) item_loop(std::integral_constant<int, 2>{}, a.n_frames);
+        else item_loop(std::integral_constant<int, 1>{}, a.n_frames * nv);
     }
     // ---- drain: per-pixel gather of the noted tiles (sampling warps only: named barrier 1) ----
     if (n_slow == 0 && u >= sp.n_units) break;  // the common case: nothing noted

@@ -143,7 +143,8 @@ class SbsWarper:
         return self._packed
 
     # --- per batch ---------------------------------------------------------------------------------------
-    _STREAM_ITEMS = 12  # (frame, eye) items per tile up to which vr180_remap streams the tiles (csrc/tiled.cu)
+    # (frame, eye) rectangles per tile up to which vr180_remap streams the tiles (csrc/tiled.cu: 20 with a shared map)
+    _STREAM_ITEMS = {True: 20, False: 12}
 
     def _source_for(self, n_frames: int) -> str:
         """The coordinate source of one call: the plan's, or for "auto" the faster one for this batch size."""
@@ -154,7 +155,7 @@ class SbsWarper:
             return "lut_packed" if has_tiled_lut else "lut"
         if self.auto_radius or not has_tiled_lut:
             return "analytic"
-        if n_frames * (2 if self.share_map else 1) > self._STREAM_ITEMS:
+        if n_frames * (2 if self.share_map else 1) > self._STREAM_ITEMS[self.share_map]:
             return "analytic"
         self._small_calls += 1  # the first small call is not worth a LUT yet (a plan used once)
         return "lut_packed" if self._small_calls > 1 or self._packed is not None else "analytic"
