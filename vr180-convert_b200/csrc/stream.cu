@@ -17,12 +17,13 @@
 //   * per tile a thread only unpacks its 4 entries into the sampling constants (offset and selectors by multiply-add,
 //     the bilinear weight pair by one LDS.64 from a table built once per CTA); no block-wide reduction, no pitch
 //     search, no per-launch-mode branches.
-// Pipeline, barriers and the sampling / re-packing of a tile are those of k_warp_tiled (tiled.cuh), with one frame of
-// one eye per item; the stage ring has fixed-size slots because consecutive items belong to different tiles.
+// Pipeline, barriers and the sampling / re-packing of a tile are those of k_warp_tiled (tiled.cuh); an item is one
+// frame of one eye -- or of both eyes when they share the coordinates and both rectangles fit a slot; the stage ring
+// has fixed-size slots because consecutive items belong to different tiles.
 // Tiles that cannot be packed (partial edge tiles, NaN / huge coordinates), whose rectangle exceeds a slot, or that
 // touch the source edge under a non-zero border are noted while the CTA streams and gathered per pixel afterwards.
-// Measured (B200): one 4K pair 24.6 us (k_warp_tiled 36-41 us), one 8K pair with per-eye maps 108 us (217 us); faster
-// than k_warp_tiled up to ~14 (frame, eye) items per tile.
+// Measured (B200): one 4K pair 24 us (k_warp_tiled 36-41 us), one 8K pair with per-eye maps 108 us (217 us); faster
+// than k_warp_tiled up to ~24 (shared map) / ~14 (per-eye maps) rectangles per tile.
 #include "tiled.cuh"
 
 namespace vr180 {
