@@ -608,7 +608,7 @@ def run_gpu(args) -> dict:
                      "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                      "algorithmic_bytes_per_launch": main["bytes_per_step"],
                      "source_touched_fraction": main["touched_fraction"],
-                     "kernel": "vr180::tiled::k_warp_tiled (1 launch per step; k_warp_stream for <= 20 / 12 (frame, eye) "
+                     "kernel": "vr180::tiled::k_warp_tiled (1 launch per step; k_warp_stream for <= 20 / 16 (frame, eye) "
                                "rectangles per tile with tile-packed LUTs)"},
         "e2e": None,
         "clocks": clocks,

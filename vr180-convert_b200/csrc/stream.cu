@@ -174,8 +174,8 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
             const int o = n_store & (kOB - 1);
             mbar_wait(s_ofull + o * 8, (uint32_t)(n_store / kOB) & 1u);
             const int4 q = s_q[s_slot];
-            tma_store_3d(&tm.dst, q.x, q.y, q.z, s_out + o * kOutItemBytes);
-            if (q.w >= 0) tma_store_3d(&tm.dst, q.w, q.y, q.z, s_out + o * kOutItemBytes + kOutTileBytes);  // the other eye
+            tma_store_3d(&tm.dst, q.x, q.y, q.z & 0xffff, s_out + o * kOutItemBytes);
+            if (q.w >= 0) tma_store_3d(&tm.dst, q.w, q.y, q.z >> 16, s_out + o * kOutItemBytes + kOutTileBytes);  // the item's second rectangle
             bulk_commit();
             bulk_wait_read<0>();
             mbar_arrive(s_oempty + o * 8);
@@ -195,29 +195,24 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
             if (!g.fast) continue;
             const int ty = tile / sp.tiles_x, tx = tile - ty * sp.tiles_x;
             const CUtensorMap* const map0 = &tm.src[grp][(g.pitch - kPitchMin) / kPitchStep][g.rsel];
-            // Both eyes of a frame share the tile's coordinates: when their two rectangles fit one slot they travel as ONE
-            // item (two box loads on one barrier, one hand-shake with the sampling warps, two tile stores).
-            const bool pair = nv == 2 && 2 * g.eye_pitch <= kSlotBytes;
+            // The tile's rectangles (frame-major, eye-minor: they all share the tile's coordinates) travel two per item when
+            // two fit one slot: two box loads on one barrier, one hand-shake with the sampling warps, two tile stores.
+            const int n_rects = a.n_frames * nv, per_item = 2 * g.eye_pitch <= kSlotBytes ? 2 : 1;
             const int x_l = (a.view[grp].dst_x_offset + tx * kTileW) * 3;
-            const int x_r = nv == 2 ? (a.view[grp + 1].dst_x_offset + tx * kTileW) * 3 : -1;
-            for (int f = 0; f < a.n_frames; ++f) {
-                for (int v = 0; v < (pair ? 1 : nv); ++v) {
-                    if (n_load - n_store == kSlots) store_next();
-                    const uint32_t bar = s_full + l_slot * 8;
-                    const uint32_t dst = s_stage + l_slot * kSlotBytes;
-                    if (pair) {
-                        s_q[l_slot] = make_int4(x_l, ty * M::kTileH, f, x_r);
-                        mbar_expect_tx(bar, 2u * (uint32_t)g.rect_bytes);
-                        tma_load_3d(dst, map0, g.bx0, g.ry0, f, bar);
-                        tma_load_3d(dst + g.eye_pitch, map0 + kWidths * kRowSizes, g.bx0, g.ry0, f, bar);
-                    } else {
-                        s_q[l_slot] = make_int4(v ? x_r : x_l, ty * M::kTileH, f, -1);
-                        mbar_expect_tx(bar, (uint32_t)g.rect_bytes);
-                        tma_load_3d(dst, map0 + v * (kWidths * kRowSizes), g.bx0, g.ry0, f, bar);
-                    }
-                    ++n_load;
-                    if (++l_slot == kSlots) l_slot = 0;
-                }
+            const int x_r = nv == 2 ? (a.view[grp + 1].dst_x_offset + tx * kTileW) * 3 : x_l;
+            for (int r = 0; r < n_rects; r += per_item) {
+                if (n_load - n_store == kSlots) store_next();
+                const uint32_t bar = s_full + l_slot * 8;
+                const uint32_t dst = s_stage + l_slot * kSlotBytes;
+                const bool two = per_item == 2 && r + 1 < n_rects;
+                const int v0 = nv == 2 ? (r & 1) : 0, f0 = nv == 2 ? (r >> 1) : r;
+                const int v1 = nv == 2 ? ((r + 1) & 1) : 0, f1 = nv == 2 ? ((r + 1) >> 1) : r + 1;
+                s_q[l_slot] = make_int4(v0 ? x_r : x_l, ty * M::kTileH, f0 | (f1 << 16), two ? (v1 ? x_r : x_l) : -1);
+                mbar_expect_tx(bar, (two ? 2u : 1u) * (uint32_t)g.rect_bytes);
+                tma_load_3d(dst, map0 + v0 * (kWidths * kRowSizes), g.bx0, g.ry0, f0, bar);
+                if (two) tma_load_3d(dst + g.eye_pitch, map0 + v1 * (kWidths * kRowSizes), g.bx0, g.ry0, f1, bar);
+                ++n_load;
+                if (++l_slot == kSlots) l_slot = 0;
             }
         }
         while (n_store < n_load) store_next();
@@ -302,9 +297,9 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
             pc[0].ws = smem_u32(slot);
         }
 
-        const bool pair = nv == 2 && 2 * g.eye_pitch <= kSlotBytes;  // as the producer decides
-        auto item_loop = [&](auto eyes_tag, int n_items) {
-            constexpr int EYES = decltype(eyes_tag)::value;
+        const int n_rects = a.n_frames * nv, per_item = 2 * g.eye_pitch <= kSlotBytes ? 2 : 1;  // as the producer decides
+        auto item_loop = [&](auto rects_tag, int n_items) {
+            constexpr int EYES = decltype(rects_tag)::value;  // rectangles of an item
 #pragma unroll 1
             for (int it = 0; it < n_items; ++it) {
                 mbar_wait(s_full + st * 8, ph);
@@ -319,7 +314,7 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
                         const uint32_t r = M::sample(buf + v * g.eye_pitch, pc[k], (uint32_t)g.pitch);
                         word[k] = __byte_perm(r, __shfl_down_sync(0xffffffffu, r, 1), out_sel);
                     }
-                    // (after the first eye's sampling, which does not need the out buffer yet)
+                    // (after the first rectangle's sampling, which does not need the out buffer yet)
                     if (v == 0 && n >= kOB) mbar_wait(s_oempty + o * 8, (uint32_t)(n / kOB + 1) & 1u);  // store n - kOB has read out[o]
                     if (flags & 1u) {
 #pragma unroll
@@ -333,8 +328,12 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
                 if (++st == kSlots) { st = 0; ph ^= 1u; }
             }
         };
-        if (pair) item_loop(std::integral_constant<int, 2>{}, a.n_frames);
-        else item_loop(std::integral_constant<int, 1>{}, a.n_frames * nv);
+        if (per_item == 2 && n_rects > 1) {
+            item_loop(std::integral_constant<int, 2>{}, n_rects >> 1);
+            if (n_rects & 1) item_loop(std::integral_constant<int, 1>{}, 1);
+        } else {
+            item_loop(std::integral_constant<int, 1>{}, n_rects);
+        }
     }
     // ---- drain: per-pixel gather of the noted tiles (sampling warps only: named barrier 1) ----
     if (n_slow == 0 && u >= sp.n_units) break;  // the common case: nothing noted
@@ -354,6 +353,7 @@ k_warp_stream(const __grid_constant__ RemapArgs a, const __grid_constant__ Strea
 template <class M, int CTAS>
 static int launch_stream_mode(const RemapArgs& a, const short* tab, cudaStream_t st) {
     const int n_groups = a.share_map ? 1 : a.n_views;
+    if (a.n_frames > 0x7fff) return VR180_ERR_UNSUPPORTED;  // an item's two frame indices travel in one int
     const TmaMaps* tm = tma_maps_for(a, M::kInterp, M::kRowsMin, M::kTileH, 1);
     if (!tm) return VR180_ERR_UNSUPPORTED;
     static std::atomic<int> attr_done[64];

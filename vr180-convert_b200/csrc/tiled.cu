@@ -1088,11 +1088,11 @@ int launch_remap_tiled(const RemapArgs& a0, int channels, int interp, const vr18
     if (n_dyn != 0 && n_dyn != n_groups) return VR180_ERR_UNSUPPORTED;
     const bool dyn = n_dyn != 0;
     // A few frames per launch with tile-packed LUTs: little to amortise a tile's prologue over -> persistent CTAs that
-    // stream the tiles (stream.cu).  Measured, B200, streamed vs batched: 4K pairs sharing a map (both eyes of a frame =
-    // one item) 1 / 2 / 4 / 8 / 12 / 16 pairs 24.1 / 36.9 / 60.2 / 109 / 158 / 208 us vs 36.3 / 45.7 / 78.5 / 116 / 155 / 196 us;
-    // 8K pairs with per-eye maps (one item per frame) 1 / 2 / 4 / 8 / 16 pairs 110 / 153 / 258 / 477 / 911 us vs
-    // 217 / 245 / 310 / 548 / 821 us.  VR180_TILED_DEBUG bit 1: whenever eligible; bit 2: never.
-    const int kStreamMaxItems = a0.share_map ? 20 : 12;  // (frame, eye) rectangles per tile
+    // stream the tiles (stream.cu), two of a tile's (frame, eye) rectangles per pipeline item.  Measured, B200, streamed vs
+    // batched: 4K pairs sharing a map 1 / 2 / 4 / 8 / 12 / 16 pairs 24.0 / 36.9 / 60.2 / 109 / 158 / 208 us vs 36.3 / 45.7 /
+    // 78.5 / 116 / 155 / 196 us; 8K pairs with per-eye maps 1 / 2 / 4 / 8 / 12 / 16 / 24 pairs 110 / 151 / 240 / 431 / 618 / 806 /
+    // 1206 us vs 217 / 245 / 310 / 548 / 690 / 827 / 1125 us.  VR180_TILED_DEBUG bit 1: whenever eligible; bit 2: never.
+    const int kStreamMaxItems = a0.share_map ? 20 : 16;  // (frame, eye) rectangles per tile
     {
         bool all_packed = !dyn;
         for (int g = 0; g < n_groups; ++g) all_packed = all_packed && a0.view[g].packed != nullptr;

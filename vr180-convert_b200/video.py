@@ -144,7 +144,7 @@ class SbsWarper:
 
     # --- per batch ---------------------------------------------------------------------------------------
     # (frame, eye) rectangles per tile up to which vr180_remap streams the tiles (csrc/tiled.cu: 20 with a shared map)
-    _STREAM_ITEMS = {True: 20, False: 12}
+    _STREAM_ITEMS = {True: 20, False: 16}
 
     def _source_for(self, n_frames: int) -> str:
         """The coordinate source of one call: the plan's, or for "auto" the faster one for this batch size."""
