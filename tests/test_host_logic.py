@@ -235,3 +235,33 @@ def test_argument_validation_without_gpu():
     assert handle.vr180_build_map(None, 4, 4, None, None, 4, None) == -1
     assert handle.vr180_remap(None, None) == -1
     assert handle.vr180_ctx_run(None, None) == -1
+
+
+def test_sbs_warper_auto_source_policy():
+    """SbsWarper(map_source="auto") picks the coordinate source per call from the batch size alone (no GPU needed to
+    check the policy): batches analytic, a plan's second and later small calls its tile-packed LUT, per-frame auto radius
+    always analytic, user-defined transformers always a LUT."""
+    from vr180_convert_b200.video import SbsWarper
+
+    def plan(**kw):
+        p = object.__new__(SbsWarper)
+        p.map_source, p.channels, p._lowerable, p.auto_radius, p.share_map = "auto", 3, True, False, True
+        p._small_calls, p._packed = 0, None
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    p = plan()
+    assert p._source_for(64) == "analytic" and p._small_calls == 0      # 128 rectangles per tile: a batch
+    assert p._source_for(1) == "analytic"                               # first small call: not worth a LUT yet
+    assert p._source_for(10) == "lut_packed"                            # 20 rectangles per tile with a shared map: small
+    assert p._source_for(11) == "analytic"
+    q = plan(share_map=False)
+    assert q._source_for(16) == "analytic" and q._source_for(16) == "lut_packed" and q._source_for(17) == "analytic"
+    assert plan(auto_radius=True)._source_for(1) == "analytic"
+    r = plan(auto_radius=True)
+    assert [r._source_for(1) for _ in range(3)] == ["analytic"] * 3
+    assert plan(_lowerable=False)._source_for(64) == "lut_packed"
+    assert plan(_lowerable=False, channels=1)._source_for(1) == "lut"
+    assert plan(channels=4)._source_for(1) == "analytic"
+    assert plan(map_source="lut_fixed")._source_for(1) == "lut_fixed"
