@@ -350,23 +350,30 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
             } else if (sc.valid) {  // straight-line: the same op functions, in the same order, as the interpreter would run
                 // instantiated once per chain so that R, the polynomial and the denormalisation are read with static
                 // constant-bank operands (no indexed LDC, no register copies)
+                // (one pixel at a time, not unrolled: the chain is ~700 instructions per pixel, and a CTA that serves one
+                // frame runs it exactly once -- unrolled over the thread's pixels it is 48 KB of instruction fetch per tile)
                 auto std_eval = [&](const StdChain& c) {
-#pragma unroll
+#pragma unroll 1
                     for (int k = 0; k < kPx; ++k) {
                         ChainState s;
                         seed(k, s);
                         if (c.has_rot) op_rot3(c.R, s);
                         if (c.n_poly >= 0) op_poly(c.poly, c.n_poly, s);
                         op_fisheye_dec(VR180_MAP_EQUIDISTANT, s);
+                        double ox = 0.0, oy = 0.0;
+                        int qx = 0, qy = 0;
                         if (dyn) {
                             to_xy(s);
-                            nx[k] = s.x;
-                            ny[k] = s.y;
+                            ox = s.x;
+                            oy = s.y;
                         } else {
                             op_denormalize(c.den, s);
-                            sx[k] = M::quant(__double2float_rn(s.x));  // astype(float32) then cvRound(x * 32)
-                            sy[k] = M::quant(__double2float_rn(s.y));
+                            qx = M::quant(__double2float_rn(s.x));  // astype(float32) then cvRound(x * 32)
+                            qy = M::quant(__double2float_rn(s.y));
                         }
+#pragma unroll
+                        for (int kk = 0; kk < kPx; ++kk)  // (no indexed register arrays)
+                            if (kk == k) { sx[kk] = qx; sy[kk] = qy; nx[kk] = ox; ny[kk] = oy; }
                     }
                 };
                 if (mv.chain_idx) std_eval(tp.std[1]);
