@@ -11,7 +11,9 @@ HBM (torch CUDA tensors are only the buffer type) is warped by one kernel launch
   * map_source="auto" (default): "analytic" for batches; a plan with a fixed radius that is called again and again
     with one or a few pairs (a frame-at-a-time video loop) builds the tile-packed LUT on its second such call and
     serves them from it -- vr180_remap then streams the tiles through persistent CTAs (csrc/stream.cu): a 4K pair
-    takes 25 us instead of 60 us, an 8K pair 110 us instead of ~300 us.  Costs 12 bytes of HBM per output pixel and map;
+    takes 25 us instead of 60 us, an 8K pair 110 us instead of ~300 us.  Costs 12 bytes of HBM per output pixel and map.
+    (Capturing calls in a CUDA graph: pass the source explicitly, or let the plan build its LUT -- `packed_lut()` --
+    before the capture, so that no LUT construction lands inside the graph);
   * radius="auto": k_get_radius per frame (max over the two eyes) feeds the warp kernel through device memory.
 
 Frames of a clip are independent, so multi-GPU runs shard them statically with `shard_range` (no collective).
