@@ -28,6 +28,7 @@ namespace {
 
 constexpr int kSlots = 3;
 constexpr size_t kChunkBytes = (size_t)192 << 20;  // source + destination bytes per pipeline chunk
+constexpr size_t kBandBytes = (size_t)8 << 20;     // rows packed and uploaded as one band of the first chunk
 constexpr size_t kCopyUnit = (size_t)1 << 20;      // bytes one copy-thread task moves
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -450,7 +451,10 @@ static int ctx_run_locked(vr180_ctx* c, const vr180_host_job_t* job) {
         const int s = k % kSlots, f0 = k * chunk, nf = std::min(chunk, F - f0);
         Slot& sl = c->slot[s];
         // --- pack (pageable sources): copy threads fill the slot's pinned buffer while the GPU runs chunk k - 1 --
-        if (stage_in) {
+        // The first chunk has nothing to hide behind (and a single pair -- apply_lr on two arrays -- IS one chunk): it is
+        // packed and uploaded in bands of rows, so that the DMA of a band runs while the copy threads pack the next one.
+        const bool banded = stage_in && k == 0;
+        if (stage_in && !banded) {
             if (k >= kSlots) VR180_CUDA(cudaEventSynchronize(sl.ev_h2d));  // the slot's previous upload has left it
             std::vector<Copy2D> cp;
             for (int v = 0; v < V; ++v)
@@ -461,7 +465,20 @@ static int ctx_run_locked(vr180_ctx* c, const vr180_host_job_t* job) {
         }
         // --- upload -------------------------------------------------------------------------------------
         if (k >= kSlots) VR180_CUDA(cudaStreamWaitEvent(c->s_h2d, sl.ev_comp, 0));  // slot's previous compute done
-        for (int v = 0; v < V; ++v) {
+        if (banded) {
+            const size_t band_rows = std::max<size_t>(1, kBandBytes / std::max<size_t>(src_pitch, 1));
+            for (int v = 0; v < V; ++v)
+                for (int f = 0; f < nf; ++f)
+                    for (size_t r0 = 0; r0 < (size_t)job->src_rows; r0 += band_rows) {
+                        const size_t nr = std::min(band_rows, (size_t)job->src_rows - r0);
+                        uint8_t* hp = (uint8_t*)sl.h_src[v].p + (size_t)f * src_frame + r0 * src_pitch;
+                        run_copies(*pool, {{hp, src_of(v, f0 + f) + r0 * (size_t)job->src_pitch[v], src_pitch,
+                                            (size_t)job->src_pitch[v], src_row, nr}});
+                        VR180_CUDA(cudaMemcpyAsync((uint8_t*)sl.src[v].p + (size_t)f * src_frame + r0 * src_pitch, hp,
+                                                   nr * src_pitch, cudaMemcpyHostToDevice, c->s_h2d));
+                    }
+        }
+        for (int v = 0; v < V && !banded; ++v) {
             uint8_t* dp = (uint8_t*)sl.src[v].p;
             if (stage_in) {
                 VR180_CUDA(cudaMemcpyAsync(dp, sl.h_src[v].p, src_frame * nf, cudaMemcpyHostToDevice, c->s_h2d));
