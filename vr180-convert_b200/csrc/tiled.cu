@@ -76,7 +76,10 @@ struct TileGeom {
 //                              (item n - OB), so a warp can run at most OB items ahead of the slowest one
 // SPLIT: the descriptors' boxes are ONE frame deep (a launch with per-frame radii needs those for its mixed chunks), so
 // an FR-frame item of an equal-radii chunk is fetched and stored as FR boxes on the same barrier / in the same bulk group.
-template <class M, int NV, bool DYN, int FR, bool SPLIT = false>  // FR: frames per item (2: one box load / tile store / barrier round per 2 frames)
+// VPAIR (with SPLIT, FR == 2, NV == 2): the item's two rectangles are the two EYES of one frame instead of two frames of
+// one eye -- for launches whose CTAs get a single frame (one stereo pair per call): one barrier round per frame, and
+// per-row state (Lanczos4's weights) serves both eyes.
+template <class M, int NV, bool DYN, int FR, bool SPLIT = false, bool VPAIR = false>  // FR: frames per item (2: one box load / tile store / barrier round per 2 frames)
 __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm, int v_begin, int f0, int f1,
                                            const typename M::Pixel (&pc)[M::kPx], const TileGeom& tg, const int pitch,
                                            uint8_t* smem, int band, int cg, const DynRadius& dr,
@@ -95,7 +98,8 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     int2* const s_org = reinterpret_cast<int2*>(smem + Lay<M>::kOffOrg);
     // item n = FR consecutive frames of one view; a chunk with an odd frame count ends with a phantom frame: the
     // host keeps chunks even, so it lies past the end of the batch, where TMA loads zeros and drops the store
-    const int n_items = ((f1 - f0 + FR - 1) / FR) * NV;
+    static_assert(!VPAIR || (SPLIT && FR == 2 && NV == 2 && !DYN), "an eye pair is two one-frame boxes of two views");
+    const int n_items = VPAIR ? (f1 - f0) : ((f1 - f0 + FR - 1) / FR) * NV;
     const int rsel = tg.nrows <= M::kRowsMin ? 0 : (tg.nrows - M::kRowsMin + kRowsStep - 1) / kRowsStep;
     const int rect_bytes = (M::kRowsMin + rsel * kRowsStep) * pitch;  // one frame's box; multiple of 64
     const int stage_bytes = FR * rect_bytes;                          // bytes the box load(s) of an item deliver
@@ -112,7 +116,8 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
         int p_item = 0, p_stage = 0;  // next item to fetch and its stage
         auto load = [&]() {
             const uint32_t bar = s_full + p_stage * 8;
-            const int v = (NV == 2) ? (p_item & 1) : 0, f = f0 + FR * ((NV == 2) ? (p_item >> 1) : p_item);
+            const int v = (NV == 2 && !VPAIR) ? (p_item & 1) : 0;
+            const int f = VPAIR ? f0 + p_item : f0 + FR * ((NV == 2) ? (p_item >> 1) : p_item);
             int bx0 = tg.bx0, ry0 = tg.ry0;
             if (DYN) {  // this frame's rectangle; its origin travels to the samplers next to the stage
                 const double rad = __ldg(dr.radius + f);
@@ -131,8 +136,8 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
             if (SPLIT) {
 #pragma unroll
                 for (int fr = 0; fr < FR; ++fr)  // a frame past the batch is all zero fill, and still rect_bytes on the barrier
-                    tma_load_3d(s_stage + p_stage * stage_stride + fr * frame_pitch, map0 + v * (kWidths * kRowSizes), bx0, ry0,
-                                f + fr, bar);
+                    tma_load_3d(s_stage + p_stage * stage_stride + fr * frame_pitch,
+                                map0 + (VPAIR ? fr : v) * (kWidths * kRowSizes), bx0, ry0, VPAIR ? f : f + fr, bar);
             } else {
                 tma_load_3d(s_stage + p_stage * stage_stride, map0 + v * (kWidths * kRowSizes), bx0, ry0, f, bar);
             }
@@ -142,13 +147,15 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
         for (int n = 0; n < S && n < n_items; ++n) load();  // fill the ring
         for (int n = 0; n < n_items; ++n) {
             const int o = n & (OB - 1);
-            const int v = (NV == 2) ? (n & 1) : 0, f = f0 + FR * ((NV == 2) ? (n >> 1) : n);
+            const int v = (NV == 2 && !VPAIR) ? (n & 1) : 0;
+            const int f = VPAIR ? f0 + n : f0 + FR * ((NV == 2) ? (n >> 1) : n);
             mbar_wait(s_ofull + o * 8, (uint32_t)(n / OB) & 1u);  // every sampling warp has written item n
             if (n + S < n_items) load();  // ofull(n) also means: every warp has left the stage of item n -> re-fill it
             if (SPLIT) {
 #pragma unroll
                 for (int fr = 0; fr < FR; ++fr)
-                    tma_store_3d(&tm.dst, v ? dst_x1 : dst_x0, tg.y0, f + fr, s_out + o * kOutItemBytes + fr * kOutTileBytes);
+                    tma_store_3d(&tm.dst, (VPAIR ? fr : v) ? dst_x1 : dst_x0, tg.y0, VPAIR ? f : f + fr,
+                                 s_out + o * kOutItemBytes + fr * kOutTileBytes);
             } else {
                 tma_store_3d(&tm.dst, v ? dst_x1 : dst_x0, tg.y0, f, s_out + o * kOutItemBytes);
             }
@@ -549,10 +556,12 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         return M::kRowsMin + (rows <= M::kRowsMin ? 0 : (rows - M::kRowsMin + kRowsStep - 1) / kRowsStep) * kRowsStep;
     };
     // (a chunk with varying radii runs one-frame items; FR-frame items of a DYN launch are FR one-frame boxes, each 128-byte aligned)
-    const int fr_item = dynr ? 1 : FR;
+    // (a launch that gives its CTAs single frames pairs the two eyes of a shared map in one item: see VPAIR)
+    const bool vpair = !DYN && FR == 1 && nv == 2;
+    const int fr_item = dynr ? 1 : (vpair ? 2 : FR);
     auto stage_fits = [&](int rows, int pitch_bytes) {
         const int rect = box_rows_of(rows) * pitch_bytes;
-        return ((fr_item * (DYN ? (rect + 127) & ~127 : rect) + 127) & ~127) <= Lay<M>::kStageArea;
+        return ((fr_item * ((DYN || vpair) ? (rect + 127) & ~127 : rect) + 127) & ~127) <= Lay<M>::kStageArea;
     };
     // Any other border (a colour, REPLICATE, REFLECT, WRAP, REFLECT_101) needs real taps or the border colour where the
     // footprint leaves the source: those tiles take the per-pixel path below; tiles inside the source never see a border.
@@ -712,8 +721,13 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         else         frame_loop<M, 1, DYN, 1>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
     } else {
         // (a DYN launch has one-frame boxes: its equal-radii chunks run FR-frame items as FR boxes each)
-        if (nv == 2) frame_loop<M, 2, false, FR, DYN>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
-        else         frame_loop<M, 1, false, FR, DYN>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
+        if constexpr (!DYN && FR == 1) {
+            if (nv == 2) frame_loop<M, 2, false, 2, true, true>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
+            else         frame_loop<M, 1, false, 1, false>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
+        } else {
+            if (nv == 2) frame_loop<M, 2, false, FR, DYN>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
+            else         frame_loop<M, 1, false, FR, DYN>(a, tm, v_begin, f0, f1, pc, tg, pitch, smem, band, cg, dr, nx, ny, tp.tab);
+        }
     }
 }
 
