@@ -400,6 +400,10 @@ def warp_host(
     del keep
     if trans is not None and (trans < 0).any():
         raise IndexError("index 0 is out of bounds for axis 0 with size 0")  # get_radius found no transition
+    if trans is not None and LOG.isEnabledFor(20):
+        for f in range(n_frames):
+            r = max((int(trans[f, v, 1]) - int(trans[f, v, 0])) / 2 for v in range(n_views))
+            LOG.info(f"Radius: {r}, strategy: auto, image shape: {(rows, cols, ch)}")
     if squeeze:
         outs = [o[:, :, 0] for o in outs]
     return outs if batched else outs[0]
@@ -620,11 +624,22 @@ def lr_frame(transformer, left, right, *, size_output=(2048, 2048), interpolatio
         return np.concatenate(halves, axis=1)
 
     if isinstance(transformer, tuple):  # per-eye transformer: own radius and own map per eye (remapper.py:460-473)
-        radii = [get_radius_smart(radius, [eye]) for eye in eyes]
+        if isinstance(radius, str) and radius == "auto":  # both eyes' scan lines in ONE upload / launch / read
+            radii = _device_radius(eyes)
+            for eye, r in zip(eyes, radii):
+                LOG.info(f"Radius: {r}, strategy: {radius}, image shape: {np.asarray(eye).shape}")
+        else:
+            radii = [get_radius_smart(radius, [eye]) for eye in eyes]
         if same_shape and (fused_merge or not merge):
             return warp_host(list(transformer), eyes, radii=radii, share_map=False, merge=fused_merge, **kw)
         # eyes of different geometry (unequal crops): the reference runs apply() per eye with that eye's size_input
         return finish([warp_host([t], [eye], radii=[r], share_map=True, **kw) for t, eye, r in zip(transformer, eyes, radii)])
+    if (isinstance(radius, str) and radius == "auto" and same_shape and (fused_merge or not merge)
+            and np.asarray(eyes[0]).ndim == 3
+            and transformer.lower(shape=(int(size_output[1]), int(size_output[0]))) is not None):
+        # one radius = max over both eyes (remapper.py:82-84, :475-484), scanned and consumed on the device inside the
+        # job: no separate upload / launch / blocking read for the two scan lines
+        return warp_host([transformer], eyes, radii=[1.0], share_map=True, auto_radius=True, merge=fused_merge, **kw)
     radius_ = get_radius_smart(radius, eyes)  # one radius = max over both eyes, ONE map (remapper.py:475-484)
     if same_shape and (fused_merge or not merge):
         return warp_host([transformer], eyes, radii=[radius_], share_map=True, merge=fused_merge, **kw)
