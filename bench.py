@@ -67,6 +67,9 @@ WORKLOADS = {
     "8k_pair_lut_linear": dict(n=4096, interp=1, tuple_=True, chain="rot_poly", src="lut_packed", radius="fixed", pairs=1,
                                desc="ONE 8K pair per launch (2x4096^2 -> 8192x4096), per-eye rotation + PolynomialScaler, cached "
                                     "tile-packed LUTs: the tile-streaming kernel [BASELINE configs[2], unbatched video loop]"),
+    "8k_pair_linear": dict(n=4096, interp=1, tuple_=True, chain="rot_poly", src="analytic", radius="fixed", pairs=1,
+                           desc="ONE 8K pair per launch, per-eye rotation + PolynomialScaler, fused analytic (no LUT): one "
+                                "apply_lr call of the reference [BASELINE configs[2], unbatched]"),
     "8k_nearest_fixed": dict(n=4096, interp=0, tuple_=False, chain="base", src="analytic", radius="fixed", pairs=16,
                              desc="batched 8K pairs, base chain, fused analytic, INTER_NEAREST, fixed radius (the pipeline "
                                   "without the interpolation arithmetic)"),

@@ -20,7 +20,7 @@ INCLUDE = PKG.parent / "include"
 LIB = PKG / "libvr180_b200.so"
 OBJ_DIR = PKG / "build"
 SOURCES = ["kernels.cu", "tiled.cu", "stream.cu", "api.cu", "pipeline.cu", "codec.cu"]
-HEADERS = ["chain.cuh", "sampler.cuh", "tables.cuh", "common.cuh", "tiled.cuh"]
+HEADERS = ["chain.cuh", "chain_fast.cuh", "sampler.cuh", "tables.cuh", "common.cuh", "tiled.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -273,6 +273,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
              const __grid_constant__ vr180_chain_t chain1, const __grid_constant__ TiledParams tp,
              const __grid_constant__ TmaMaps tm) {
     constexpr int kPx = M::kPx;
+    constexpr int kChainUnroll = (FR == 1 && !DYN && kPx >= 2) ? 2 : 1;  // pixels of a thread whose chains are interleaved
     constexpr int kWarpsPerBand = 4 / kPx;  // a band = 4 output rows x 32 columns = 4 / kPx warps of 8 kPx columns
     extern __shared__ __align__(1024) uint8_t smem[];
     double* s_trig = reinterpret_cast<double*>(smem + Lay<M>::kOffTrig);  // [4][32]
@@ -322,6 +323,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     if (mv.map_kind == VR180_MAPSRC_ANALYTIC) {
         const vr180_chain_t& ch = mv.chain_idx ? chain1 : chain0;
         const StdChain& sc = tp.std[mv.chain_idx ? 1 : 0];
+        const bool fastc = sc.valid && sc.fast && !(tp.debug & 256);  // VR180_TILED_DEBUG bit 8: op-by-op evaluation (run_ops)
         if (sc.valid || tp.sep_prefix) {
             // Normalize + EquirectangularEncoder prefix (transformer.py:153-164, :545-566): the angle of a column
             // (row) depends on the column (row) only, so its sincos is evaluated once per tile column (row).
@@ -333,8 +335,12 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                 const double n = mul_rn(__ddiv_rn(add_rn(c, -(is_row ? nm[1] : nm[0])), nm[2]), 2.0);
                 double sv, cv;
                 sincos(mul_rn(n, kHalfPi), &sv, &cv);
-                s_trig[(is_row ? 64 : 0) + idx] = sv;
-                s_trig[(is_row ? 96 : 32) + idx] = cv;
+                if (fastc) {  // the rotation folded into per-column / per-row terms (chain_fast.cuh)
+                    std_tables(sc.R, sc.lat_is_y != 0, is_row, sv, cv, s_trig, s_trig + 128, idx);
+                } else {
+                    s_trig[(is_row ? 64 : 0) + idx] = sv;
+                    s_trig[(is_row ? 96 : 32) + idx] = cv;
+                }
             }
             __syncthreads();
             const bool lat_is_y = ch.ops[1].iparam != 0;
@@ -354,29 +360,25 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                 }
             };
             if (!sampler) {
-            } else if (sc.valid) {  // straight-line: the same op functions, in the same order, as the interpreter would run
-                // instantiated once per chain so that R, the polynomial and the denormalisation are read with static
-                // constant-bank operands (no indexed LDC, no register copies)
-                // (one pixel at a time, not unrolled: the chain is ~700 instructions per pixel, and a CTA that serves one
-                // frame runs it exactly once -- unrolled over the thread's pixels it is 48 KB of instruction fetch per tile)
+            } else if (fastc) {  // the standard chain, folded (chain_fast.cuh)
+                // instantiated once per chain so that the polynomial and the denormalisation are read with static
+                // constant-bank operands (no indexed LDC, no register copies); one pixel at a time, not unrolled: a CTA
+                // that serves one frame runs this exactly once, and instruction fetch is what such a launch waits for
                 auto std_eval = [&](const StdChain& c) {
-#pragma unroll 1
+#pragma unroll(kChainUnroll)
                     for (int k = 0; k < kPx; ++k) {
-                        ChainState s;
-                        seed(k, s);
-                        if (c.has_rot) op_rot3(c.R, s);
-                        if (c.n_poly >= 0) op_poly(c.poly, c.n_poly, s);
-                        op_fisheye_dec(VR180_MAP_EQUIDISTANT, s);
-                        double ox = 0.0, oy = 0.0;
+                        const int xi = c.lat_is_y ? prow(k) : pcol(k), yi = c.lat_is_y ? pcol(k) : prow(k);
+                        StdSeed sd;
+                        sd.scale = s_trig[xi]; sd.b0 = s_trig[32 + xi]; sd.b1 = s_trig[64 + xi]; sd.b2 = s_trig[96 + xi];
+                        sd.a0 = s_trig[128 + yi]; sd.a1 = s_trig[160 + yi]; sd.a2 = s_trig[192 + yi];
+                        double ox, oy;
                         int qx = 0, qy = 0;
                         if (dyn) {
-                            to_xy(s);
-                            ox = s.x;
-                            oy = s.y;
+                            std_pixel<true>(sd, c.poly, c.n_poly, c.den, ox, oy);
                         } else {
-                            op_denormalize(c.den, s);
-                            qx = M::quant(__double2float_rn(s.x));  // astype(float32) then cvRound(x * 32)
-                            qy = M::quant(__double2float_rn(s.y));
+                            std_pixel<false>(sd, c.poly, c.n_poly, c.den, ox, oy);
+                            qx = M::quant(__double2float_rn(ox));  // astype(float32) then cvRound(x * 32)
+                            qy = M::quant(__double2float_rn(oy));
                         }
 #pragma unroll
                         for (int kk = 0; kk < kPx; ++kk)  // (no indexed register arrays)
@@ -891,6 +893,20 @@ static void match_std_chain(const vr180_chain_t& c, tiled::StdChain& out) {
         return;
     memcpy(out.den, c.ops[k + 1].p, sizeof(out.den));
     out.valid = 1;
+    // chain_fast.cuh takes theta from (hypot(vx, vy), vz) as a point of the unit circle: R has to be orthonormal
+    if (!out.has_rot) {
+        out.R[0] = out.R[4] = out.R[8] = 1.0;
+        out.fast = 1;
+    } else {
+        double err = 0.0;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double d = i == j ? -1.0 : 0.0;
+                for (int m = 0; m < 3; ++m) d += out.R[3 * m + i] * out.R[3 * m + j];
+                err = std::fmax(err, std::fabs(d));
+            }
+        out.fast = err < 1e-12 ? 1 : 0;  // (NaN -> 0)
+    }
 }
 
 // ---- TMA descriptors (host) ---------------------------------------------------------------------------------

@@ -4,12 +4,13 @@
 #pragma once
 #include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint
 
+#include <cmath>
 #include <cstdlib>
 #include <mutex>
 #include <type_traits>
 #include <vector>
 
-#include "chain.cuh"
+#include "chain_fast.cuh"
 #include "common.cuh"
 #include "sampler.cuh"
 
@@ -38,7 +39,7 @@ struct Lay {
     static constexpr int kOutArea = M::kOutTiles * M::kTileH * kTileW * 3;
     static constexpr int kOffOut = kStageArea;
     static constexpr int kOffTrig = kOffOut + kOutArea;
-    static constexpr int kOffRed = kOffTrig + 4 * 32 * 8;
+    static constexpr int kOffRed = kOffTrig + 7 * 32 * 8;  // double[4][32] sincos of the tile's columns / rows, or chain_fast.cuh's tables [4 + 3][32]
     static constexpr int kOffBar = kOffRed + 8 * 4 * 4;  // full[kMaxStages], empty[kMaxStages], ofull[kOutBufs], oempty[kOutBufs]
     static constexpr int kOffOrg = kOffBar + (2 * kMaxStages + 2 * kOutBufs) * 8;  // int2 origin of the rectangle in each stage
     static constexpr int kOffExt = kOffOrg + kMaxStages * 8;                         // double[8][4] per-warp normalised extremes
@@ -56,6 +57,7 @@ constexpr int kStreamSlotBytes = (M::kStageArea / 3) & ~127;
 //   Denormalize
 struct StdChain {
     int valid, lat_is_y, has_rot, n_poly;
+    int fast, pad_;   // R orthonormal (identity without a rotation): the folded evaluation of chain_fast.cuh applies
     double norm[3];   // cx, cy, scale
     double R[9];
     double poly[VR180_MAX_OP_PARAMS];
