@@ -143,9 +143,7 @@ __device__ __forceinline__ double theta_unit(double vz, double h) {
 // Per-tile tables of the folded rotation (see above): side X carries {scale, B0, B1, B2}, side Y carries {A0, A1, A2};
 // X = rows when the latitude runs along y (EquirectangularEncoder's default), else columns.
 //   v = scale A + B
-struct StdSeed {
-    double scale, b0, b1, b2, a0, a1, a2;
-};
+constexpr int kStdTableDoubles = 7 * 32;  // x_side[4][32] (scale, B0, B1, B2), y_side[3][32] (A0, A1, A2)
 __device__ __forceinline__ void std_tables(const double* R, bool lat_is_y, bool is_row, double sv, double cv, double* x_side,
                                            double* y_side, int idx) {
     // lat_is_y:  v = (c_row s_col, s_row, c_row c_col):  A_k = R[3k] s_col + R[3k+2] c_col (columns),  B_k = R[3k+1] s_row, scale c_row (rows)
@@ -165,10 +163,11 @@ __device__ __forceinline__ void std_tables(const double* R, bool lat_is_y, bool 
     }
 }
 
-// One pixel of the standard chain.  normalised: stop before Denormalize (per-frame radius: the caller applies it).
+// One pixel of the standard chain from its rotated unit vector v = scale A + B.  NORMALISED: stop before Denormalize
+// (per-frame radius: the caller applies it).
 template <bool NORMALISED>
-__device__ __forceinline__ void std_pixel(const StdSeed& s, const double* poly, int n_poly, const double* den, double& ox, double& oy) {
-    const double vx = fma(s.scale, s.a0, s.b0), vy = fma(s.scale, s.a1, s.b1), vz = fma(s.scale, s.a2, s.b2);
+__device__ __forceinline__ void std_pixel(double vx, double vy, double vz, const double* poly, int n_poly, const double* den,
+                                          double& ox, double& oy) {
     const double h2 = fma(vx, vx, vy * vy);
     double ux = 0.0, uy = 1.0, h = h2;  // atan2(0, 0) = 0 -> (sin, cos) = (0, 1); a NaN h2 reaches theta
     if (h2 > 0.0) {

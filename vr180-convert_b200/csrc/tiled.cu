@@ -365,18 +365,29 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
                 // constant-bank operands (no indexed LDC, no register copies); one pixel at a time, not unrolled: a CTA
                 // that serves one frame runs this exactly once, and instruction fetch is what such a launch waits for
                 auto std_eval = [&](const StdChain& c) {
+                    // v = scale A + B (chain_fast.cuh).  A thread's pixels share their column (row patches) or their row
+                    // (8 x 4 patches): that side of the table is read once, the other per pixel -- these are 8-byte
+                    // loads on the pipe that bounds the kernel
+                    const bool x_fixed = M::kRowPatch ? !c.lat_is_y : (c.lat_is_y != 0);  // side X = rows iff lat_is_y
+                    const int fi = M::kRowPatch ? lx : ly;
+                    const double* const ft = s_trig + (x_fixed ? 0 : 128) + fi;
+                    const double f0 = ft[0], f1 = ft[32], f2 = ft[64], f3 = x_fixed ? ft[96] : 0.0;
 #pragma unroll(kChainUnroll)
                     for (int k = 0; k < kPx; ++k) {
-                        const int xi = c.lat_is_y ? prow(k) : pcol(k), yi = c.lat_is_y ? pcol(k) : prow(k);
-                        StdSeed sd;
-                        sd.scale = s_trig[xi]; sd.b0 = s_trig[32 + xi]; sd.b1 = s_trig[64 + xi]; sd.b2 = s_trig[96 + xi];
-                        sd.a0 = s_trig[128 + yi]; sd.a1 = s_trig[160 + yi]; sd.a2 = s_trig[192 + yi];
+                        const int vi = M::kRowPatch ? prow(k) : pcol(k);
+                        double vx, vy, vz;
+                        if (x_fixed) {  // (uniform)
+                            vx = fma(f0, s_trig[128 + vi], f1); vy = fma(f0, s_trig[160 + vi], f2); vz = fma(f0, s_trig[192 + vi], f3);
+                        } else {
+                            const double sc_ = s_trig[vi];
+                            vx = fma(sc_, f0, s_trig[32 + vi]); vy = fma(sc_, f1, s_trig[64 + vi]); vz = fma(sc_, f2, s_trig[96 + vi]);
+                        }
                         double ox, oy;
                         int qx = 0, qy = 0;
                         if (dyn) {
-                            std_pixel<true>(sd, c.poly, c.n_poly, c.den, ox, oy);
+                            std_pixel<true>(vx, vy, vz, c.poly, c.n_poly, c.den, ox, oy);
                         } else {
-                            std_pixel<false>(sd, c.poly, c.n_poly, c.den, ox, oy);
+                            std_pixel<false>(vx, vy, vz, c.poly, c.n_poly, c.den, ox, oy);
                             qx = M::quant(__double2float_rn(ox));  // astype(float32) then cvRound(x * 32)
                             qy = M::quant(__double2float_rn(oy));
                         }
