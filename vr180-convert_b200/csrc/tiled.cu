@@ -9,8 +9,8 @@
 // for every frame of its frame chunk:
 //   prologue   coordinates of the tile's pixels, once: analytic chain in float64 (row / column sincos of the
 //              Normalize + EquirectangularEncoder prefix are separable and computed 64x per tile instead of
-//              2048x; the standard chain shape runs as straight-line code, anything else through the op
-//              interpreter of chain.cuh), or float32 maps, or the fixed-point LUT; quantised exactly like
+//              2048x; the standard chain shape runs in the folded form of chain_fast.cuh, anything else through
+//              the op interpreter of chain.cuh), or float32 maps, or the fixed-point LUT; quantised exactly like
 //              cv::remap (sampler.cuh); per pixel only {smem offset of the first tap, byte shift, packed integer
 //              weights} stay in registers.
 //   bbox       block-wide min / max of the integer source coordinates -> the tile's source rectangle.
