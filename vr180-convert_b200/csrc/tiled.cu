@@ -106,7 +106,10 @@ __device__ __forceinline__ void frame_loop(const RemapArgs& a, const TmaMaps& tm
     // distance of an item's frames inside a stage: packed by a box FR frames deep; one-frame boxes land 128-byte aligned
     const int frame_pitch = SPLIT ? (rect_bytes + 127) & ~127 : rect_bytes;
     const int stage_stride = (FR * frame_pitch + 127) & ~127;         // TMA destinations are 128-byte aligned
-    const int S = min(kMaxStages, Lay<M>::kStageArea / stage_stride);
+    // stages that fit the staging area: both are multiples of 128 bytes, and the +0.5 keeps the approximate float quotient
+    // of the two small integers on the right side of every integer (an integer division is ~20 instructions)
+    static_assert(Lay<M>::kStageArea % 128 == 0 && Lay<M>::kStageArea / 128 <= 1024, "float quotient below");
+    const int S = min(kMaxStages, (int)__fdividef((float)(Lay<M>::kStageArea / 128) + 0.5f, (float)(stage_stride >> 7)));
 
     if (warp == kSamplers / 32) {  // ---- producer ----
         if (lane != 0) return;
@@ -273,7 +276,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
              const __grid_constant__ vr180_chain_t chain1, const __grid_constant__ TiledParams tp,
              const __grid_constant__ TmaMaps tm) {
     constexpr int kPx = M::kPx;
-    constexpr int kChainUnroll = (FR == 1 && !DYN && kPx >= 2) ? 2 : 1;  // pixels of a thread whose chains are interleaved
+    constexpr int kChainUnroll = (FR == 1 && !DYN) ? kPx : 1;  // pixels of a thread whose chains are interleaved
     constexpr int kWarpsPerBand = 4 / kPx;  // a band = 4 output rows x 32 columns = 4 / kPx warps of 8 kPx columns
     extern __shared__ __align__(1024) uint8_t smem[];
     double* s_trig = reinterpret_cast<double*>(smem + Lay<M>::kOffTrig);  // [4][32]
@@ -290,12 +293,16 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     }
     int* const s_cost = reinterpret_cast<int*>(smem + Lay<M>::kOffCost);  // wavefront cost of each candidate pitch
     if (tid < kPitchCands) s_cost[tid] = 0;
-    const int tx = blockIdx.x % tp.tiles_x, ty = blockIdx.x / tp.tiles_x;
+    // grid = (tiles_x, tiles_y, map groups x frame chunks): no division by a runtime tile count in a CTA that may live for
+    // one frame only
+    const int tx = blockIdx.x, ty = blockIdx.y, tile = ty * tp.tiles_x + tx;  // tile: index into a tile-packed LUT
     const int x0 = tx * kTileW, y0 = ty * M::kTileH;
-    const int g = blockIdx.y;  // map group: the view whose coordinates drive this CTA
+    const bool two_groups = !a.share_map && a.n_views == 2;
+    const int g = two_groups ? (int)(blockIdx.z & 1u) : 0;  // map group: the view whose coordinates drive this CTA
+    const int chunk = two_groups ? (int)(blockIdx.z >> 1) : (int)blockIdx.z;
     const ViewArgs& mv = a.view[g];
     const int v_begin = g, v_end = a.share_map ? a.n_views : g + 1, nv = v_end - v_begin;
-    const int f0 = blockIdx.z * a.frames_per_cta, f1 = min(a.n_frames, f0 + a.frames_per_cta);
+    const int f0 = chunk * a.frames_per_cta, f1 = min(a.n_frames, f0 + a.frames_per_cta);
     const bool sampler = warp < kSamplers / 32;  // the last warp = TMA producer: no pixels of its own
     const int sw = warp & (kSamplers / 32 - 1), band = sw / kWarpsPerBand, cg = sw % kWarpsPerBand;
     // pixel k of this thread (tile-local): 8 x 4 patches: column lx + 8 k, row ly; row patches: column lane, row 4 band + k
@@ -308,7 +315,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
     PackedHdr hdr;
     hdr.mnx = hdr.mxx = hdr.mny = hdr.mxy = 0;
     hdr.flags = hdr.pad = 0;
-    if (mv.map_kind != VR180_MAPSRC_ANALYTIC && mv.packed) hdr = packed_header(mv.packed, blockIdx.x);
+    if (mv.map_kind != VR180_MAPSRC_ANALYTIC && mv.packed) hdr = packed_header(mv.packed, tile);
     const bool packed_tile = (hdr.flags & 1) != 0;  // CTA-uniform: coordinates and bounding box come from the packed LUT
 
     // ---- coordinates of this thread's pixels --------------------------------------------------------------
@@ -429,7 +436,7 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         bool unpacked = false;
         {
             if (packed_tile) {
-                const uint32_t* ent = packed_entries(mv.packed, tp.n_tiles) + ((size_t)blockIdx.x * kSamplers + tid) * kPx;
+                const uint32_t* ent = packed_entries(mv.packed, tp.n_tiles) + ((size_t)tile * kSamplers + tid) * kPx;
                 uint32_t e[kPx];
                 if constexpr (kPx == 4) {
                     const uint4 v = __ldg(reinterpret_cast<const uint4*>(ent));
@@ -548,15 +555,15 @@ k_warp_tiled(const __grid_constant__ RemapArgs a, const __grid_constant__ vr180_
         mny = hdr.mny;
         mxy = hdr.mxy;
     } else {
-        mnx = mny = INT_MAX;
-        mxx = mxy = INT_MIN;
-#pragma unroll
-        for (int w = 0; w < kSamplers / 32; ++w) {
-            mnx = min(mnx, s_red[w * 4 + 0]);
-            mxx = max(mxx, s_red[w * 4 + 1]);
-            mny = min(mny, s_red[w * 4 + 2]);
-            mxy = max(mxy, s_red[w * 4 + 3]);
-        }
+        // lane w holds the box of sampling warp w: one 128-bit load + four warp reductions (a loop over the 8 records
+        // is 64 instructions per thread, and a one-frame tile has few to amortise them over)
+        static_assert(Lay<M>::kOffRed % 16 == 0, "s_red is read as int4");
+        int4 r = make_int4(INT_MAX, INT_MIN, INT_MAX, INT_MIN);
+        if (lane < kSamplers / 32) r = reinterpret_cast<const int4*>(s_red)[lane];
+        mnx = __reduce_min_sync(0xffffffffu, r.x);
+        mxx = __reduce_max_sync(0xffffffffu, r.y);
+        mny = __reduce_min_sync(0xffffffffu, r.z);
+        mxy = __reduce_max_sync(0xffffffffu, r.w);
     }
     // taps cover columns ix - kLo .. ix + kHi and rows iy - kLo .. iy + kHi
     const int bx0 = (3 * (mnx - M::kLo)) & ~15, bx1 = (3 * (mxx + M::kHi + 1) + 15) & ~15;  // 16-byte granules
@@ -1084,7 +1091,8 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
     fpc = (fpc + FR - 1) / FR * FR;  // chunks start at multiples of FR: phantom frames can only lie past the batch
     a.frames_per_cta = fpc;
     const int chunks = (a.n_frames + fpc - 1) / fpc;
-    if (chunks > 65535 || tiles_x * (long long)tiles_y > 0x7fffffffLL) return VR180_ERR_UNSUPPORTED;
+    if (n_groups > 2 || chunks * n_groups > 65535 || tiles_y > 65535 || tiles_x * (long long)tiles_y > 0x7fffffffLL)
+        return VR180_ERR_UNSUPPORTED;
     auto is_sep = [](const vr180_chain_t& c) {
         return c.n_ops >= 2 && c.ops[0].code == VR180_OP_NORMALIZE && c.ops[1].code == VR180_OP_EQUIRECT_ENC;
     };
@@ -1095,7 +1103,7 @@ static int launch_mode(const RemapArgs& a0, const vr180_chain_t& c0, const vr180
         if (!is_sep(c)) tp.sep_prefix = 0;
         match_std_chain(c, tp.std[a.view[g].chain_idx ? 1 : 0]);
     }
-    dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)n_groups, (unsigned)chunks);
+    dim3 grid((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)(n_groups * chunks));  // z = chunk * n_groups + map group
     k_warp_tiled<M, DYN, FR><<<grid, kThreads, Lay<M>::kSmemBytes, st>>>(a, c0, c1, tp, tm);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     VR180_CUDA(cudaGetLastError());
