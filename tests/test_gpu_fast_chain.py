@@ -121,3 +121,29 @@ def test_fast_chain_per_frame_radius(flags):
         m = chain_np.get_map(ops(Q1), radius=radius, size_input=(hin, win), size_output=(wout, hout))
         want = np.concatenate([cv2.remap(ln[f], m[0], m[1], interpolation=1), cv2.remap(rn[f], m[0], m[1], interpolation=1)], axis=1)
         assert np.array_equal(got[f], want), (f, radius, int((got[f] != want).sum()))
+
+
+def test_non_orthonormal_matrix_keeps_the_op_by_op_chain():
+    """A `rot3` matrix that is not a rotation (only reachable by lowering to the C ABI by hand: here a 3 % shear-and-scale)
+    makes (hypot(vx, vy), vz) leave the unit circle, so the folded theta would be wrong by percents: the host detects it
+    (|R^T R - I| >= 1e-12) and the kernel evaluates arccos(vz) op by op, as the reference would with such a matrix."""
+    import torch
+
+    M = chain_np.quat_to_matrix(*Q2) @ np.array([[1.03, 0.01, 0.0], [0.0, 0.98, 0.0], [0.0, 0.02, 1.0]])
+
+    @__import__("attrs").define()
+    class Sheared(V.Euclidean3DRotator):
+        def lower(self, shape=None, inverse=False):
+            return [("rot3", M.reshape(-1).tolist())]
+
+    t = V.EquirectangularEncoder() * Sheared(V.quaternion(*Q2)) * V.PolynomialScaler(POLY) * V.FisheyeDecoder("equidistant")
+    ops = [("equirect_enc", True), ("rot3", M.ravel().tolist()), ("poly", POLY), ("fisheye_dec", "equidistant")]
+    hin, win, wout, hout = 500, 520, 640, 480
+    ln, rn = _noise(29, 3, hin, win)
+    wp = V.SbsWarper(t, size_input=(hin, win), size_output=(wout, hout), interpolation=1, radius=255.0, map_source="analytic")
+    got = wp(torch.from_numpy(ln).cuda(), torch.from_numpy(rn).cuda()).cpu().numpy()
+    m = chain_np.get_map(ops, radius=255.0, size_input=(hin, win), size_output=(wout, hout))
+    assert np.isnan(m[0]).any()  # |vz| > 1 somewhere: np.arccos gives NaN there, and so must the kernel (border colour)
+    for f in range(3):
+        want = np.concatenate([cv2.remap(ln[f], m[0], m[1], interpolation=1), cv2.remap(rn[f], m[0], m[1], interpolation=1)], axis=1)
+        assert np.array_equal(got[f], want), (f, int((got[f] != want).sum()))
