@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: scripts/gpu_final.sh TAG -- what the driver runs at round end (GPU tests, smoke, default bench line, reference arm)
+# usage: scripts/gpu_final_full.sh TAG -- what the driver runs at round end (GPU tests, smoke, default bench line, reference arm)
 # + memcheck of the folded-chain tests + ncu --set full of the headline kernel + the launch list of the same command
 TAG=$1
 mkdir -p gpurun_out

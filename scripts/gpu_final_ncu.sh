@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: scripts/gpu_final3.sh TAG -- folded-chain tests, then ncu --set full of the headline kernel and of the analytic 4K pair, and the launch list of the default bench command
+# usage: scripts/gpu_final_ncu.sh TAG -- folded-chain tests, then ncu --set full of the headline kernel and of the analytic 4K pair, and the launch list of the default bench command
 TAG=$1
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_fast_chain.py -x -q 2>&1 | tail -3

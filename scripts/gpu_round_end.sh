@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: scripts/gpu_final2.sh TAG -- what the driver runs at round end: GPU tests, smoke, the default bench line
+# usage: scripts/gpu_round_end.sh TAG -- what the driver runs at round end: GPU tests, smoke, the default bench line
 TAG=$1
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/${TAG}_tests.log
