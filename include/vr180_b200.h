@@ -361,6 +361,9 @@ int vr180_debug_weight_table(int K, int16_t* out);
    the tile-streaming kernel (0 = 3 per SM) -- lets tests push hundreds of tiles through one CTA.  Returns the
    previous value. */
 int vr180_debug_set(int what, int value);
+/* The byte mover of the pipeline's copy threads (packs pageable frames into the page-locked ring: streaming stores for
+   copies of 8 KB and more on CPUs with AVX2, memcpy otherwise; VR180_NT_COPY=0 forces memcpy) applied to caller buffers. */
+int vr180_debug_host_copy(void* dst, const void* src, size_t bytes);
 /* Copy-only ceiling of the host-buffer pipeline (bench.py e2e.copy_ceiling): page-locked host <-> device copies of
    `bytes` each way, `reps` times, no kernel: out_gbs[4] = {H2D alone, D2H alone, H2D and D2H while both run}. */
 int vr180_debug_copy_ceiling(int device, size_t bytes, int reps, double* out_gbs);

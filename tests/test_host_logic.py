@@ -265,3 +265,21 @@ def test_sbs_warper_auto_source_policy():
     assert plan(_lowerable=False, channels=1)._source_for(1) == "lut"
     assert plan(channels=4)._source_for(1) == "analytic"
     assert plan(map_source="lut_fixed")._source_for(1) == "lut_fixed"
+
+
+def test_host_copy_moves_every_byte_at_every_alignment():
+    """The copy threads' byte mover (csrc/hostcopy.cpp: streaming stores behind an aligned head, memcpy tail) against
+    NumPy slices: every source / destination misalignment 0..33, sizes around the 8 KB switch and the 128-byte blocks;
+    the bytes next to the destination range stay untouched."""
+    import ctypes as C
+
+    lib = N.lib()
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 256, 1 << 18, dtype=np.uint8)
+    for n in (0, 1, 31, 127, 128, 8191, 8192, 8193, 8192 + 127, 65536 + 5, 200_003):
+        for so, do in ((0, 0), (1, 0), (0, 1), (3, 29), (31, 32), (33, 17), (7, 64)):
+            dst = np.full(n + 256, 0xA5, np.uint8)
+            rc = lib.vr180_debug_host_copy(C.c_void_p(dst.ctypes.data + do), C.c_void_p(src.ctypes.data + so), n)
+            assert rc == 0
+            assert np.array_equal(dst[do:do + n], src[so:so + n]), (n, so, do)
+            assert (dst[:do] == 0xA5).all() and (dst[do + n:] == 0xA5).all(), (n, so, do)

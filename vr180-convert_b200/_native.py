@@ -107,6 +107,7 @@ SYMBOLS = {
     "vr180_debug_weight_table": (C.c_int, [C.c_int, C.c_void_p]),
     "vr180_debug_set": (C.c_int, [C.c_int, C.c_int]),
     "vr180_debug_copy_ceiling": (C.c_int, [C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
+    "vr180_debug_host_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
 }
 
 _lib = None

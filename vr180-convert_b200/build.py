@@ -20,6 +20,8 @@ INCLUDE = PKG.parent / "include"
 LIB = PKG / "libvr180_b200.so"
 OBJ_DIR = PKG / "build"
 SOURCES = ["kernels.cu", "tiled.cu", "stream.cu", "api.cu", "pipeline.cu", "codec.cu"]
+HOST_SOURCES = ["hostcopy.cpp"]  # plain C++ with per-file ISA flags (g++), linked into the same library
+HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-mavx2"]
 HEADERS = ["chain.cuh", "chain_fast.cuh", "sampler.cuh", "tables.cuh", "common.cuh", "tiled.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -39,9 +41,9 @@ def _nvcc() -> str:
 
 def _fingerprint() -> str:
     h = hashlib.sha256()
-    for f in [*(CSRC / s for s in SOURCES), *(CSRC / s for s in HEADERS), INCLUDE / "vr180_b200.h"]:
+    for f in [*(CSRC / s for s in SOURCES), *(CSRC / s for s in HOST_SOURCES), *(CSRC / s for s in HEADERS), INCLUDE / "vr180_b200.h"]:
         h.update(f.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + HOST_FLAGS).encode())
     return h.hexdigest()
 
 
@@ -64,8 +66,19 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed for {src}")
         return obj
 
+    def compile_host(src: str) -> Path:
+        obj = OBJ_DIR / (Path(src).stem + ".o")
+        cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+        r = subprocess.run([cxx, *HOST_FLAGS, "-c", str(CSRC / src), "-o", str(obj)], capture_output=True, text=True)
+        if verbose or r.returncode:
+            sys.stderr.write(r.stderr)
+        if r.returncode:
+            raise RuntimeError(f"{cxx} failed for {src}")
+        return obj
+
     with ThreadPoolExecutor(len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
+    objs += [compile_host(s) for s in HOST_SOURCES]
     cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-cudart", "static", "-ldl",
            "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -22,6 +22,9 @@
 
 #include "common.cuh"
 
+namespace vr180 {
+void stream_copy_avx2(uint8_t* d, const uint8_t* s, size_t n);  // hostcopy.cpp (g++ -mavx2)
+}
 using namespace vr180;
 
 namespace {
@@ -175,6 +178,21 @@ bool is_page_locked(const void* p) {
     return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
+// Large copies into / out of the page-locked ring: streaming stores where the CPU has them (hostcopy.cpp)
+void copy_bytes(uint8_t* dst, const uint8_t* src, size_t n) {
+    static const bool nt = [] {
+        const char* e = getenv("VR180_NT_COPY");
+        if (e && atoi(e) == 0) return false;
+#if defined(__x86_64__)
+        return __builtin_cpu_supports("avx2") != 0;
+#else
+        return false;
+#endif
+    }();
+    if (nt && n >= ((size_t)8 << 10)) stream_copy_avx2(dst, src, n);
+    else memcpy(dst, src, n);
+}
+
 // a 2-D byte copy (rows x row_bytes, independent pitches), split into ~kCopyUnit tasks
 struct Copy2D {
     uint8_t* dst;
@@ -197,9 +215,9 @@ void run_copies(CopyPool& pool, const std::vector<Copy2D>& copies) {
         const Unit& u = units[i];
         const Copy2D& k = copies[u.c];
         if (k.dst_pitch == k.row_bytes && k.src_pitch == k.row_bytes) {
-            memcpy(k.dst + u.r0 * k.dst_pitch, k.src + u.r0 * k.src_pitch, (u.r1 - u.r0) * k.row_bytes);
+            copy_bytes(k.dst + u.r0 * k.dst_pitch, k.src + u.r0 * k.src_pitch, (u.r1 - u.r0) * k.row_bytes);
         } else {
-            for (size_t r = u.r0; r < u.r1; ++r) memcpy(k.dst + r * k.dst_pitch, k.src + r * k.src_pitch, k.row_bytes);
+            for (size_t r = u.r0; r < u.r1; ++r) copy_bytes(k.dst + r * k.dst_pitch, k.src + r * k.src_pitch, k.row_bytes);
         }
     });
 }
@@ -647,6 +665,13 @@ int vr180_ctx_run(vr180_ctx_t* c, const vr180_host_job_t* job) {
             set_cuda_error(e, "cudaStreamSynchronize");
             return VR180_ERR_CUDA;
         }
+    return VR180_OK;
+}
+
+/* Test hook: the copy threads' byte mover (streaming stores for large copies, hostcopy.cpp) on caller buffers. */
+int vr180_debug_host_copy(void* dst, const void* src, size_t bytes) {
+    if ((!dst || !src) && bytes) return VR180_ERR_INVALID_ARG;
+    copy_bytes(static_cast<uint8_t*>(dst), static_cast<const uint8_t*>(src), bytes);
     return VR180_OK;
 }
 
