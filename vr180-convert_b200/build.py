@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import hashlib
 import os
+import platform
 import shutil
 import subprocess
 import sys
@@ -21,7 +22,7 @@ LIB = PKG / "libvr180_b200.so"
 OBJ_DIR = PKG / "build"
 SOURCES = ["kernels.cu", "tiled.cu", "stream.cu", "api.cu", "pipeline.cu", "codec.cu"]
 HOST_SOURCES = ["hostcopy.cpp"]  # plain C++ with per-file ISA flags (g++), linked into the same library
-HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-mavx2"]
+HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC"] + (["-mavx2"] if platform.machine() in ("x86_64", "AMD64") else [])
 HEADERS = ["chain.cuh", "chain_fast.cuh", "sampler.cuh", "tables.cuh", "common.cuh", "tiled.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

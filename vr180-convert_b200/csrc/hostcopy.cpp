@@ -7,7 +7,9 @@
 // it is overwritten -- three DRAM transfers per byte moved.  The destination here is never read by the CPU again (the DMA
 // engine reads it), so large copies use streaming stores: two transfers per byte.
 // Compiled by g++ with -mavx2 for this file only; the caller checks the CPU at run time (VR180_NT_COPY=0 disables it).
+#if defined(__x86_64__)
 #include <immintrin.h>
+#endif
 
 #include <cstddef>
 #include <cstdint>
@@ -16,6 +18,9 @@
 namespace vr180 {
 
 void stream_copy_avx2(uint8_t* d, const uint8_t* s, size_t n) {
+#if !defined(__x86_64__)
+    memcpy(d, s, n);  // (never selected: the caller's run-time check is x86 only)
+#else
     size_t head = (32 - (reinterpret_cast<uintptr_t>(d) & 31)) & 31;  // streaming stores need a 32-byte aligned destination
     if (head > n) head = n;
     if (head) {
@@ -40,6 +45,7 @@ void stream_copy_avx2(uint8_t* d, const uint8_t* s, size_t n) {
     _mm_sfence();  // the DMA engine, not this core, is the next reader
     const size_t tail = n - blocks * 128;
     if (tail) memcpy(d, s, tail);
+#endif
 }
 
 }  // namespace vr180
