@@ -7,7 +7,7 @@
 // (PolynomialScaler), :363-392 (FisheyeDecoder) and :189-204 (Denormalize).  Three algebraic foldings, each
 // within a few float64 roundings of the reference's order of operations (~1e-12 px; the float32 map the reference
 // rounds to has a spacing of 1.2e-4 .. 2.4e-4 px at 8K, and the 16.7 M coordinates of a 4096^2 map come out identical,
-// tests/test_gpu_parity.py::test_fast_chain_equals_the_op_by_op_chain):
+// tests/test_gpu_fast_chain.py::test_fast_chain_equals_the_op_by_op_chain; 1.14 G pixels of random cases: scripts/fast_chain_sweep.py):
 //   * rotation: v = (c_row s_col, s_row, c_row c_col), so R v = c_row (R0 s_col + R2 c_col) + R1 s_row -- the bracket
 //     depends on the column only and R1 s_row on the row only; both are tabulated per tile (shared memory, FP64) and a
 //     pixel costs 3 DFMA instead of 3 DMUL + 9 DMUL + 6 DADD;
